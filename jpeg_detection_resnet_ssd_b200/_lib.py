@@ -1,0 +1,297 @@
+"""ctypes binding of libssdcodec.so (include/ssdcodec.h) and the process-wide context.
+
+There is deliberately no CPU fallback: if the shared library is missing or no
+B200 is visible, every codec entry point raises `SSDCodecError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libssdcodec.so')
+
+# ---- constants mirrored from include/ssdcodec.h ------------------------------
+OK, ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_DEGENERATE, ERR_NODEVICE, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+F32, F64 = 0, 1
+COORDS = {'centroids': 0, 'minmax': 1, 'corners': 2}
+BORDER = {'half': 0, 'include': 1, 'exclude': 2}
+MODE_PER_CLASS, MODE_FAST, MODE_LAYER, MODE_LAYER_FAST = 0, 1, 2, 3
+CONVERSIONS = {'minmax2centroids': 0, 'centroids2minmax': 1, 'corners2centroids': 2,
+               'centroids2corners': 3, 'minmax2corners': 4, 'corners2minmax': 5}
+IOU_OUTER, IOU_ELEMENTWISE = 0, 1
+K_NAMES = ['decode_filter', 'plan', 'sort', 'nms', 'merge', 'enc_rowbest', 'enc_match', 'enc_write', 'thin']
+K_COUNT = len(K_NAMES)
+
+
+class SSDCodecError(RuntimeError):
+    """Raised for every failure reported by libssdcodec (code in `.code`)."""
+
+    def __init__(self, code, message):
+        super().__init__('libssdcodec error %d: %s' % (code, message))
+        self.code = code
+
+
+class DecodeParams(C.Structure):
+    _fields_ = [('mode', C.c_int32), ('input_coords', C.c_int32), ('normalize', C.c_int32),
+                ('border_pixels', C.c_int32), ('top_k', C.c_int32), ('nms_cap', C.c_int32),
+                ('log_wh', C.c_int32), ('do_nms', C.c_int32),
+                ('conf_thresh', C.c_double), ('iou_thresh', C.c_double),
+                ('img_h', C.c_double), ('img_w', C.c_double)]
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [('n_classes', C.c_int32), ('background_id', C.c_int32), ('coords', C.c_int32),
+                ('border_pixels', C.c_int32), ('matching_multi', C.c_int32), ('normalize', C.c_int32),
+                ('log_wh', C.c_int32), ('reserved', C.c_int32),
+                ('pos_iou_threshold', C.c_double), ('neg_iou_limit', C.c_double),
+                ('img_h', C.c_double), ('img_w', C.c_double)]
+
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_pi64 = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/ssdcodec.h declares
+SIGNATURES = {
+    'ssdc_version': (_i, []),
+    'ssdc_last_error': (C.c_char_p, []),
+    'ssdc_device_count': (_i, []),
+    'ssdc_init': (_i, [C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
+    'ssdc_destroy': (None, [_vp]),
+    'ssdc_ctx_num_devices': (_i, [_vp]),
+    'ssdc_synchronize': (_i, [_vp]),
+    'ssdc_launch_count': (_i64, [_vp]),
+    'ssdc_profile_enable': (_i, [_vp, _i]),
+    'ssdc_profile_read': (_i, [_vp, C.POINTER(C.c_double), _pi64]),
+    'ssdc_timer_start': (_i, [_vp]),
+    'ssdc_timer_stop': (_i, [_vp, C.POINTER(C.c_double)]),
+    'ssdc_dev_alloc': (_i, [_vp, _i, C.c_uint64, C.POINTER(_vp)]),
+    'ssdc_dev_free': (_i, [_vp, _i, _vp]),
+    'ssdc_host_alloc': (_i, [C.c_uint64, C.POINTER(_vp)]),
+    'ssdc_host_free': (_i, [_vp]),
+    'ssdc_memcpy_h2d': (_i, [_vp, _i, _vp, _vp, C.c_uint64]),
+    'ssdc_memcpy_d2h': (_i, [_vp, _i, _vp, _vp, C.c_uint64]),
+    'ssdc_decode_submit': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, C.POINTER(DecodeParams)]),
+    'ssdc_decode_collect': (_i, [_vp, _vp, _i64, _vp, _vp, _pi64]),
+    'ssdc_decode': (_i, [_vp, _vp, _i, _i64, _i64, _i, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _pi64]),
+    'ssdc_greedy_nms': (_i, [_vp, _vp, _vp, _i64, _d, _i, _i, _vp, _pi64]),
+    'ssdc_encoder_create': (_i, [_vp, _vp, _i64, _vp, C.POINTER(EncodeParams), C.POINTER(_vp)]),
+    'ssdc_encoder_destroy': (None, [_vp]),
+    'ssdc_encoder_bad_image': (_i64, [_vp]),
+    'ssdc_encode': (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    'ssdc_encoding_template': (_i, [_vp, _i64, _vp]),
+    'ssdc_iou': (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp]),
+    'ssdc_intersection_area': (_i, [_vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp]),
+    'ssdc_convert_coordinates': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
+    'ssdc_match_bipartite_greedy': (_i, [_vp, _vp, _i64, _i64, _vp]),
+    'ssdc_match_multi': (_i, [_vp, _vp, _i64, _i64, _d, _vp, _vp, _pi64]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree libssdcodec.so and declare every prototype."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SSDCodecError(ERR_NODEVICE, 'shared library %s not found; build it with '
+                                '`python -m jpeg_detection_resnet_ssd_b200.build` (there is no CPU fallback)' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def last_error():
+    msg = load_library().ssdc_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(code):
+    if code != OK:
+        raise SSDCodecError(code, last_error())
+
+
+def ptr(a):
+    """Raw data pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context(object):
+    """Owns one `ssdc_ctx` (streams, scratch, pinned staging) over a set of devices."""
+
+    def __init__(self, devices=None):
+        lib = load_library()
+        if devices is None:
+            devices = default_devices()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        check(lib.ssdc_init(arr, len(self.devices), C.byref(h)))
+        self.lib = lib
+        self.handle = h
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.ssdc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- measurement helpers (bench.py / tests) --
+    def synchronize(self):
+        check(self.lib.ssdc_synchronize(self.handle))
+
+    def launch_count(self):
+        return int(self.lib.ssdc_launch_count(self.handle))
+
+    def profile_enable(self, on=True):
+        check(self.lib.ssdc_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        ms = (C.c_double * K_COUNT)()
+        n = (C.c_int64 * K_COUNT)()
+        check(self.lib.ssdc_profile_read(self.handle, ms, n))
+        return {K_NAMES[i]: (float(ms[i]), int(n[i])) for i in range(K_COUNT)}
+
+    def timer_start(self):
+        check(self.lib.ssdc_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(self.lib.ssdc_timer_stop(self.handle, C.byref(ms)))
+        return float(ms.value)
+
+    def dev_alloc(self, nbytes, slot=0):
+        p = C.c_void_p()
+        check(self.lib.ssdc_dev_alloc(self.handle, slot, nbytes, C.byref(p)))
+        return p
+
+    def dev_free(self, p, slot=0):
+        check(self.lib.ssdc_dev_free(self.handle, slot, p))
+
+    def h2d(self, dst, src_array, slot=0):
+        check(self.lib.ssdc_memcpy_h2d(self.handle, slot, dst, ptr(src_array), src_array.nbytes))
+
+    def d2h(self, dst_array, src, slot=0):
+        check(self.lib.ssdc_memcpy_d2h(self.handle, slot, ptr(dst_array), src, dst_array.nbytes))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (freed with the array)."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib.ssdc_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    import weakref
+    weakref.finalize(arr, _free_pinned, id(buf))
+    return arr
+
+
+_PINNED = {}
+
+
+def _free_pinned(key):
+    ent = _PINNED.pop(key, None)
+    if ent is not None and _lib is not None:
+        _lib.ssdc_host_free(ent[1])
+
+
+def default_devices():
+    """SSDC_DEVICES="0,1,.." if set, else the torchrun LOCAL_RANK, else device 0."""
+    env = os.environ.get('SSDC_DEVICES')
+    if env:
+        return [int(x) for x in env.split(',') if x.strip() != '']
+    if os.environ.get('LOCAL_RANK') is not None:
+        return [int(os.environ['LOCAL_RANK'])]
+    return [0]
+
+
+_default_ctx = None
+_ctx_lock = threading.Lock()
+
+
+def get_context():
+    """Process-wide default context (created on first use)."""
+    global _default_ctx
+    with _ctx_lock:
+        if _default_ctx is None:
+            _default_ctx = Context()
+        return _default_ctx
+
+
+def set_context(ctx):
+    """Install `ctx` as the process-wide default (returns the previous one)."""
+    global _default_ctx
+    with _ctx_lock:
+        old, _default_ctx = _default_ctx, ctx
+        return old
+
+
+# ---- shared decode driver ------------------------------------------------------
+
+def run_decode(y_pred, mode, confidence_thresh, iou_threshold, top_k, input_coords, normalize_coords,
+               img_height, img_width, border_pixels, log_wh=True, nms_cap=0, do_nms=True, ctx=None):
+    """Runs libssdcodec's decode pipeline on a host array.  Returns
+    (rows (total, 6) float64, counts (B,) int32, anchor_idx (total,) int32)."""
+    ctx = ctx or get_context()
+    y = np.asarray(y_pred)
+    if y.ndim != 3 or y.shape[2] < 14:
+        raise ValueError('y_pred must have shape (batch, #boxes, #classes + 12), got {}'.format(y.shape))
+    if y.dtype == np.float32:
+        dt = F32
+    else:
+        dt = F64
+        if y.dtype != np.float64:
+            y = y.astype(np.float64)
+    y = np.ascontiguousarray(y)
+    B, A, W = y.shape
+    p = DecodeParams()
+    p.mode = mode
+    p.input_coords = COORDS[input_coords]
+    p.normalize = 1 if normalize_coords else 0
+    p.border_pixels = BORDER[border_pixels]
+    p.top_k = 0 if top_k == 'all' else int(top_k)
+    p.nms_cap = int(nms_cap)
+    p.log_wh = 1 if log_wh else 0
+    p.do_nms = 1 if do_nms else 0
+    p.conf_thresh = float(confidence_thresh)
+    p.iou_thresh = float(iou_threshold) if do_nms else 0.0
+    p.img_h = float(img_height) if normalize_coords else 1.0
+    p.img_w = float(img_width) if normalize_coords else 1.0
+    lib = ctx.lib
+    counts = np.zeros(B, dtype=np.int32)
+    total = C.c_int64(0)
+    check(lib.ssdc_decode_submit(ctx.handle, ptr(y), dt, 0, B, A, W - 12, C.byref(p)))
+    cap = B * p.top_k if p.top_k > 0 else 0
+    rows = np.empty((max(cap, 1), 6), dtype=np.float64)
+    idx = np.empty(max(cap, 1), dtype=np.int32)
+    rc = lib.ssdc_decode_collect(ctx.handle, ptr(rows), cap, ptr(counts), ptr(idx), C.byref(total))
+    if rc == ERR_CAPACITY:
+        cap = int(total.value)
+        rows = np.empty((max(cap, 1), 6), dtype=np.float64)
+        idx = np.empty(max(cap, 1), dtype=np.int32)
+        rc = lib.ssdc_decode_collect(ctx.handle, ptr(rows), cap, ptr(counts), ptr(idx), C.byref(total))
+    check(rc)
+    n = int(total.value)
+    return rows[:n], counts, idx[:n]

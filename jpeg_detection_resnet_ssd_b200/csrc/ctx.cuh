@@ -1,0 +1,149 @@
+// ctx.cuh - context, per-device state and scratch management of libssdcodec.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include <atomic>
+
+#include "../../include/ssdcodec.h"
+
+namespace ssdc {
+
+void set_error(const char* fmt, ...);
+
+#define SSDC_CUDA(call)                                                                    \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ssdc::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,             \
+                            cudaGetErrorString(_e));                                       \
+            return SSDC_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+#define SSDC_TRY(call)                                                                     \
+    do {                                                                                   \
+        int _r = (call);                                                                   \
+        if (_r != SSDC_OK) return _r;                                                      \
+    } while (0)
+
+// A device buffer that only ever grows.
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SSDC_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);   // retry without head-room
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr; cap = 0;
+            return SSDC_ERR_CUDA;
+        }
+        cap = want;
+        return SSDC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SSDC_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); p = nullptr; return SSDC_ERR_CUDA; }
+        cap = bytes;
+        return SSDC_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// State of one submitted decode on one device (results stay on the device
+// until collected).
+struct DecodeJob {
+    bool valid = false;
+    int64_t b0 = 0, B = 0, A = 0;   // image range of this device's shard
+    int C = 0, NS = 0, dtype = 0;
+    ssdc_decode_params p;
+    bool emitted = false;           // rows already written on the device
+    int64_t out_capacity = 0;       // rows the device out buffer can hold
+    int iou_f32 = 0;
+};
+
+struct DevCtx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // decode scratch
+    Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
+    PinnedBuf h_small;
+    DecodeJob job;
+    // encode scratch
+    Buf gt, gt_off, partial, matches, enc_out, enc_out2, enc_idx, enc_flags;
+    // thin ops scratch
+    Buf t0buf, t1buf, t2buf, t3buf;
+};
+
+}  // namespace ssdc
+
+struct ssdc_ctx {
+    std::vector<ssdc::DevCtx> devs;
+    std::mutex mu;
+    std::atomic<int64_t> launches{0};
+    bool profile = false;
+    double prof_ms[SSDC_K_COUNT];
+    int64_t prof_n[SSDC_K_COUNT];
+    struct ProfEv { cudaEvent_t a, b; int family; int dev; };
+    std::vector<ProfEv> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace ssdc {
+
+// RAII bracket around a kernel launch: counts it and, when profiling is on,
+// records CUDA events on the launching stream.
+struct LaunchScope {
+    ssdc_ctx* ctx; DevCtx* d; int family; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(ssdc_ctx* c, DevCtx* dev, int fam) : ctx(c), d(dev), family(fam) {
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        if (ctx->profile) {
+            a = get_ev(); b = get_ev();
+            cudaEventRecord(a, d->stream);
+        }
+    }
+    ~LaunchScope() {
+        if (ctx->profile) {
+            cudaEventRecord(b, d->stream);
+            ctx->prof_pending.push_back({a, b, family, (int)(d - ctx->devs.data())});
+        }
+    }
+    cudaEvent_t get_ev() {
+        if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
+int check_launch(const char* what);
+
+// implemented in decode.cu / encode.cu / thin.cu
+int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, int on_device,
+                      int64_t b0, int64_t B, int64_t A, int C, const ssdc_decode_params* p);
+int decode_finish_dev(ssdc_ctx* ctx, DevCtx* d, int64_t* total_rows);
+int decode_emit_all_dev(ssdc_ctx* ctx, DevCtx* d, int64_t total_rows);
+
+}  // namespace ssdc

@@ -1,0 +1,896 @@
+// decode.cu - the decode + NMS pipeline of the SSD box codec (sm_100a).
+//
+// Replaces the numpy bodies of
+//   decode_detections        /root/reference/localisation_part/ssd_encoder_decoder/ssd_output_decoder.py:111-226
+//   decode_detections_fast   .../ssd_output_decoder.py:228-333
+//   _greedy_nms/_greedy_nms2 .../ssd_output_decoder.py:77-109
+//   DecodeDetections{,Fast}  /root/reference/localisation_part/keras_layers/keras_layer_DecodeDetections{,Fast}.py
+//
+// Kernels (one family per numpy stage):
+//   D1 decode_filter_kernel : stream y_pred (B, A, C+12) once from HBM through shared memory with
+//                             128-bit coalesced loads; per (image, class) confidence threshold with
+//                             warp-ballot compaction into per-segment key lists; anchor-offset decode
+//                             of every anchor that produced a candidate.
+//      plan_kernel          : bins the segments by size into device-side work lists.
+//   D2 sort_kernel          : segmented bitonic sort by (score desc, anchor asc), persistent CTAs
+//                             pulling segments from the work lists (shared memory, global for huge).
+//   D3 nms_kernel           : greedy NMS, one warp per segment: 32 candidates per step are tested
+//                             against the kept list (shared-memory cache) and resolved among
+//                             themselves with ballots; stops at the per-segment cap.
+//   D4 count_scan_kernel +  : per image totals, exclusive scan to packed row offsets,
+//      emit_kernel            cross-class top-k (bitonic sort of composite keys) and row output.
+#include "common.cuh"
+#include "ctx.cuh"
+#include <math.h>
+
+namespace ssdc {
+
+constexpr int D1_THREADS = 256;
+constexpr int NMS_WARPS = 4;
+constexpr int NBINS = 5;          // 0: nms list, 1..4: sort bins
+constexpr int CNT_LIST = 0;       // counters[0..4]  list sizes
+constexpr int CNT_CURSOR = 8;     // counters[8..12] work cursors
+constexpr int CNT_TOTAL = 16;
+constexpr int SORT_BYTES1 = 8 * 1024, SORT_BYTES2 = 32 * 1024, SORT_BYTES3 = 128 * 1024;   // shared-memory sort bins
+
+template <typename T> struct alignas(16) SBox { T x0, y0, x1, y1; };
+
+struct DecodeArgs {
+    int A, C, W, NS, tiles, tile_rows;
+    int input_coords, log_wh, layer_assoc, ge;
+    int do_nms, K, Kseg, always_sort;
+    double iou_thr, sx, sy, d;
+    int nseg;
+};
+
+// ---------------------------------------------------------------------------
+// D1: decode + threshold + compaction
+// ---------------------------------------------------------------------------
+template <typename InT>
+__device__ __forceinline__ SBox<InT> decode_box(const InT* row, int C, const DecodeArgs& g) {
+    // row[C..C+3] offsets, row[C+4..C+7] anchor, row[C+8..C+11] variances
+    const InT o0 = row[C], o1 = row[C + 1], o2 = row[C + 2], o3 = row[C + 3];
+    const InT a0 = row[C + 4], a1 = row[C + 5], a2 = row[C + 6], a3 = row[C + 7];
+    const InT v0 = row[C + 8], v1 = row[C + 9], v2 = row[C + 10], v3 = row[C + 11];
+    SBox<InT> b;
+    if (g.input_coords == SSDC_COORDS_CENTROIDS) {
+        // ssd_output_decoder.py:175-179 (+ bounding_box_utils.py:77-80)
+        InT tw = o2 * v2, th = o3 * v3;
+        if (g.log_wh) { tw = exp_cr(tw); th = exp_cr(th); }
+        InT w = tw * a2, h = th * a3;
+        InT cx, cy;
+        if (g.layer_assoc) {   // keras_layer_DecodeDetections.py:124-125: (off * var) * size + centre
+            cx = o0 * v0 * a2 + a0;
+            cy = o1 * v1 * a3 + a1;
+        } else {               // ssd_output_decoder.py:177-178: off * (var * size) + centre
+            cx = o0 * (v0 * a2) + a0;
+            cy = o1 * (v1 * a3) + a1;
+        }
+        InT hw = w / InT(2), hh = h / InT(2);
+        b.x0 = cx - hw; b.y0 = cy - hh; b.x1 = cx + hw; b.y1 = cy + hh;
+    } else if (g.input_coords == SSDC_COORDS_MINMAX) {
+        // ssd_output_decoder.py:181-185: (xmin, xmax, ymin, ymax)
+        InT aw = a1 - a0, ah = a3 - a2;
+        InT p0 = o0 * v0 * aw + a0, p1 = o1 * v1 * aw + a1, p2 = o2 * v2 * ah + a2, p3 = o3 * v3 * ah + a3;
+        b.x0 = p0; b.x1 = p1; b.y0 = p2; b.y1 = p3;
+    } else {
+        // ssd_output_decoder.py:187-190: (xmin, ymin, xmax, ymax)
+        InT aw = a2 - a0, ah = a3 - a1;
+        b.x0 = o0 * v0 * aw + a0; b.y0 = o1 * v1 * ah + a1; b.x1 = o2 * v2 * aw + a2; b.y1 = o3 * v3 * ah + a3;
+    }
+    return b;
+}
+
+template <typename InT, bool FAST>
+__global__ void __launch_bounds__(D1_THREADS)
+decode_filter_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr,
+                     int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
+                     SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
+    typedef typename KeyOf<InT>::type KeyT;
+    constexpr int V = 16 / (int)sizeof(InT);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = g.W, C = g.C, NS = g.NS, A = g.A;
+    InT* tile = reinterpret_cast<InT*>(smem_raw);
+    const size_t tile_bytes = (((size_t)g.tile_rows * W + V) * sizeof(InT) + 15) & ~(size_t)15;
+    int* cnt_s = reinterpret_cast<int*>(smem_raw + tile_bytes);
+    int* base_s = cnt_s + NS;
+    int* woff_s = base_s + NS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_id = blockIdx.x % g.tiles;
+    const int b = blockIdx.x / g.tiles;
+    const int a0 = tile_id * g.tile_rows;
+    const int rows = min(g.tile_rows, A - a0);
+
+    // ---- stage the contiguous span of `rows` whole rows into shared memory ----
+    const InT* src = y + ((size_t)b * A + a0) * W;
+    const int n = rows * W;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(InT)) % V);
+    InT* dst = tile + mis;                       // smem offset keeps the global 16-byte phase
+    const int head = min(n, (V - mis) % V);
+    const int nvec = (n - head) / V;
+    const int tail0 = head + nvec * V;
+    if (tid < head) dst[tid] = src[tid];
+    for (int e = tail0 + tid; e < n; e += D1_THREADS) dst[e] = src[e];
+    {
+        const int4* g4 = reinterpret_cast<const int4*>(src + head);
+        int4* s4 = reinterpret_cast<int4*>(dst + head);
+        constexpr int U = 8;
+        for (int i0 = tid; i0 < nvec; i0 += D1_THREADS * U) {
+            int4 r[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                int idx = i0 + k * D1_THREADS;
+                if (idx < nvec) r[k] = ldg_stream(g4 + idx);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                int idx = i0 + k * D1_THREADS;
+                if (idx < nvec) s4[idx] = r[k];
+            }
+        }
+    }
+    for (int s = tid; s < NS; s += D1_THREADS) cnt_s[s] = 0;
+    __syncthreads();
+
+    const bool valid = tid < rows;
+    const InT* row = dst + (size_t)(valid ? tid : 0) * W;
+    const int a = a0 + tid;
+    const unsigned lt = (1u << lane) - 1u;
+
+    bool any = false;
+    InT fbest = InT(0);
+    int fcls = 0;
+    if (FAST) {
+        // ssd_output_decoder.py:292-293 (np.argmax = first maximum, NaN wins), :324-325
+        InT best = row[0];
+        bool nan = best != best;
+        int cls = 0;
+        for (int c = 1; c < C; ++c) {
+            InT v = row[c];
+            nan |= (v != v);
+            if (v > best) { best = v; cls = c; }
+        }
+        bool pass = valid && !nan && cls != 0 && (g.ge ? (best >= thr) : (best > thr));
+        fbest = best; fcls = cls; any = pass;
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m && lane == 0) woff_s[warp] = atomicAdd(&cnt_s[0], __popc(m));
+    } else {
+        // ssd_output_decoder.py:207-209
+        for (int c = 1; c < C; ++c) {
+            InT v = row[c];
+            bool pass = valid && (g.ge ? (v >= thr) : (v > thr));
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (lane == 0) woff_s[warp * NS + c - 1] = atomicAdd(&cnt_s[c - 1], __popc(m));
+                any |= pass;
+            }
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < NS; s += D1_THREADS) {
+        int cnt = cnt_s[s];
+        base_s[s] = cnt ? atomicAdd(&seg_count[(size_t)b * NS + s], cnt) : 0;
+    }
+    __syncthreads();
+    if (FAST) {
+        unsigned m = __ballot_sync(0xffffffffu, any);
+        if (any) {
+            int pos = base_s[0] + woff_s[warp] + __popc(m & lt);
+            keys[(size_t)b * A + pos] = KeyT::make(fbest, (uint32_t)a);
+            aux_class[(size_t)b * A + a] = fcls;
+        }
+    } else {
+        for (int c = 1; c < C; ++c) {
+            InT v = row[c];
+            bool pass = valid && (g.ge ? (v >= thr) : (v > thr));
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                int pos = base_s[c - 1] + woff_s[warp * NS + c - 1] + __popc(m & lt);
+                keys[((size_t)b * NS + c - 1) * A + pos] = KeyT::make(v, (uint32_t)a);
+            }
+        }
+    }
+    if (any) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
+}
+
+// ---------------------------------------------------------------------------
+// plan: bin the non-empty segments into work lists
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int warp_append(int* counter, bool want) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void plan_kernel(const int* __restrict__ seg_count, int nseg, int* __restrict__ kept_count,
+                            int* __restrict__ lists, int* __restrict__ counters, int n1, int n2, int n3) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (s < nseg) ? seg_count[s] : 0;
+    if (s < nseg) kept_count[s] = 0;
+    int bin = 0;
+    if (n > n3) bin = 4; else if (n > n2) bin = 3; else if (n > n1) bin = 2; else if (n > 32) bin = 1;
+    int pos = warp_append(&counters[CNT_LIST + 0], n > 0);
+    if (n > 0) lists[pos] = s;
+#pragma unroll
+    for (int k = 1; k < NBINS; ++k) {
+        int p = warp_append(&counters[CNT_LIST + k], bin == k);
+        if (bin == k) lists[(size_t)k * nseg + p] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// D2: segmented sort (persistent CTAs over a work list)
+// ---------------------------------------------------------------------------
+template <typename KeyT, bool IN_SMEM>
+__global__ void sort_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count,
+                            const int* __restrict__ list, int* __restrict__ counters, int bin,
+                            DecodeArgs g, KeyT* __restrict__ scratch, int scratch_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_idx;
+    KeyT* s = IN_SMEM ? reinterpret_cast<KeyT*>(smem_raw) : scratch + (size_t)blockIdx.x * scratch_stride;
+    const int total = counters[CNT_LIST + bin];
+    for (;;) {
+        if (threadIdx.x == 0) s_idx = atomicAdd(&counters[CNT_CURSOR + bin], 1);
+        __syncthreads();
+        const int idx = s_idx;
+        __syncthreads();
+        if (idx >= total) break;
+        const int seg = list[idx];
+        const int n = seg_count[seg];
+        const int N = pow2_ceil(n);
+        const bool by_anchor = !g.do_nms && (g.K <= 0 || n <= g.K);
+        KeyT* gk = keys + (size_t)seg * g.A;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s[i] = (i < n) ? gk[i] : KeyT::lowest();
+        __syncthreads();
+        block_bitonic_sort(s, N, by_anchor);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) gk[i] = s[i];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// D3: greedy NMS, one warp per segment
+// ---------------------------------------------------------------------------
+template <typename StoreT, typename IouT>
+__device__ __forceinline__ Box<IouT> load_box(const SBox<StoreT>* __restrict__ bx, uint32_t anchor,
+                                              IouT sx, IouT sy, IouT d) {
+    SBox<StoreT> s = bx[anchor];
+    return make_box<IouT>((IouT)s.x0 * sx, (IouT)s.y0 * sy, (IouT)s.x1 * sx, (IouT)s.y1 * sy, d);
+}
+
+template <typename IouT, bool TF>
+__device__ __forceinline__ bool suppresses(const Box<IouT>& kept, const Box<IouT>& cand, IouT thr) {
+    if (TF) {
+        return false;
+    } else {
+        // kept iff `similarities <= iou_threshold` (ssd_output_decoder.py:91); NaN => dropped
+        return !(iou_boxes<IouT>(cand, kept) <= thr);
+    }
+}
+template <>
+__device__ __forceinline__ bool suppresses<float, true>(const Box<float>& kept, const Box<float>& cand, float thr) {
+    return iou_tf(cand, kept) > thr;
+}
+
+template <typename StoreT, typename IouT, typename KeyT, bool TF>
+__global__ void __launch_bounds__(NMS_WARPS * 32)
+nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __restrict__ kept_count,
+           const int* __restrict__ list, int* __restrict__ counters,
+           const SBox<StoreT>* __restrict__ boxes, DecodeArgs g, int KS) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Box<IouT>* cache = reinterpret_cast<Box<IouT>*>(smem_raw) + (size_t)warp * (KS + 32);
+    Box<IouT>* tile = cache + KS;
+    const int total = counters[CNT_LIST + 0];
+    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
+    const unsigned lt = (1u << lane) - 1u;
+
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&counters[CNT_CURSOR + 0], 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= total) break;
+        const int seg = list[idx];
+        const int b = seg / g.NS;
+        const int n = seg_count[seg];
+        const int cap = (g.Kseg > 0) ? min(g.Kseg, n) : n;
+        KeyT* kp = keys + (size_t)seg * g.A;
+        const SBox<StoreT>* bx = boxes + (size_t)b * g.A;
+        const bool tiny = n <= 32;
+
+        if (!g.do_nms) {
+            // `if iou_threshold:` falsy (ssd_output_decoder.py:326): every candidate is kept.
+            if (tiny) {
+                const bool by_anchor = (g.K <= 0 || n <= g.K);
+                KeyT k = (lane < n) ? kp[lane] : KeyT::lowest();
+                k = warp_sort(k, by_anchor);
+                if (lane < n) kp[lane] = k;
+            }
+            if (lane == 0) kept_count[seg] = cap;
+            continue;
+        }
+
+        int nkept = 0;
+        for (int t0 = 0; t0 < n && nkept < cap; t0 += 32) {
+            const int i = t0 + lane;
+            KeyT key = (i < n) ? kp[i] : KeyT::lowest();
+            if (tiny) key = warp_sort(key, false);       // small segments are sorted in registers
+            const bool valid = i < n;
+            Box<IouT> me;
+            if (valid) me = load_box<StoreT, IouT>(bx, key.anchor(), sx, sy, d);
+            else { me.x0 = me.y0 = me.x1 = me.y1 = me.area = IouT(0); }
+            bool alive = valid;
+
+            // against everything kept so far
+            for (int k = 0; k < nkept; ++k) {
+                if (!__any_sync(0xffffffffu, alive)) break;
+                Box<IouT> kb;
+                if (k < KS) kb = cache[k];
+                else kb = load_box<StoreT, IouT>(bx, kp[k].anchor(), sx, sy, d);
+                if (alive && suppresses<IouT, TF>(kb, me, thr)) alive = false;
+            }
+
+            // among the 32 candidates of this step, in canonical order
+            tile[lane] = me;
+            __syncwarp();
+            unsigned m = __ballot_sync(0xffffffffu, alive);
+            unsigned rem = m;
+            while (rem) {
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                if (nkept + __popc(m & ((1u << j) - 1u)) >= cap) {   // box j would exceed the cap
+                    m &= (1u << j) - 1u;
+                    alive = alive && (lane < j);
+                    break;
+                }
+                Box<IouT> kb = tile[j];
+                if (lane > j && alive && suppresses<IouT, TF>(kb, me, thr)) alive = false;
+                m = __ballot_sync(0xffffffffu, alive);
+                rem &= m;
+            }
+            const int pos = nkept + __popc(m & lt);
+            if (alive) {
+                if (pos < KS) cache[pos] = me;
+                kp[pos] = key;
+            }
+            nkept += __popc(m);
+            __syncwarp();
+        }
+        if (lane == 0) kept_count[seg] = nkept;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// D4: per-image totals + scan, cross-class top-k, row output
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+count_scan_kernel(const int* __restrict__ kept_count, int B, int NS, int K,
+                  int* __restrict__ out_count, long long* __restrict__ row_offset) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        long long c = 0;
+        if (b < B) {
+            long long t = 0;
+            for (int s = 0; s < NS; ++s) t += kept_count[(size_t)b * NS + s];
+            c = (K > 0 && t > K) ? K : t;
+            out_count[b] = (int)c;
+        }
+        long long x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long yv = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += yv;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long yv = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += yv;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? warp_sums[warp - 1] : 0) + (x - c);
+        if (b < B) row_offset[b] = before;
+        __syncthreads();
+        if (tid == 1023) carry = before + c;
+        __syncthreads();
+    }
+    if (tid == 0) row_offset[B] = carry;
+}
+
+template <typename KeyT> __device__ __forceinline__ double score_from_bits(uint64_t bits);
+template <> __device__ __forceinline__ double score_from_bits<Key64>(uint64_t bits) { return (double)unord32((uint32_t)bits); }
+template <> __device__ __forceinline__ double score_from_bits<Key128>(uint64_t bits) { return unord64(bits); }
+
+template <typename StoreT, typename IouT>
+__device__ __forceinline__ void write_row(double* __restrict__ rows, int* __restrict__ anchors, long long r,
+                                          int cls, double score, uint32_t anchor,
+                                          const SBox<StoreT>* __restrict__ bx, IouT sx, IouT sy) {
+    SBox<StoreT> s = bx[anchor];
+    double* o = rows + r * 6;
+    o[0] = (double)cls;
+    o[1] = score;
+    o[2] = (double)((IouT)s.x0 * sx);
+    o[3] = (double)((IouT)s.y0 * sy);
+    o[4] = (double)((IouT)s.x1 * sx);
+    o[5] = (double)((IouT)s.y1 * sy);
+    anchors[r] = (int)anchor;
+}
+
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_SMEM_KEYS = 4096;
+
+template <typename StoreT, typename IouT, typename KeyT>
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
+            const int* __restrict__ out_count, const long long* __restrict__ row_offset,
+            const SBox<StoreT>* __restrict__ boxes, const int* __restrict__ aux_class, DecodeArgs g,
+            Key128* __restrict__ merge_scratch, int merge_stride,
+            double* __restrict__ rows, int* __restrict__ anchors) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int NS = g.NS;
+    const int cnt = out_count[b];
+    if (cnt == 0) return;
+    const long long off = row_offset[b];
+    const SBox<StoreT>* bx = boxes + (size_t)b * g.A;
+    const int* cls_of = aux_class ? aux_class + (size_t)b * g.A : nullptr;
+    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy;
+
+    // total kept over the image's segments
+    long long T = 0;
+    for (int s = 0; s < NS; ++s) T += kept_count[(size_t)b * NS + s];
+
+    if (T <= cnt && !g.always_sort) {
+        // no truncation: classes ascending, inside a class the NMS keep order
+        // (ssd_output_decoder.py:212-218)
+        long long base = 0;
+        for (int s = 0; s < NS; ++s) {
+            const int k = kept_count[(size_t)b * NS + s];
+            const KeyT* kp = keys + ((size_t)b * NS + s) * g.A;
+            for (int r = threadIdx.x; r < k; r += EMIT_THREADS) {
+                KeyT key = kp[r];
+                uint32_t anchor = key.anchor();
+                int cls = (NS > 1) ? (s + 1) : cls_of[anchor];
+                write_row<StoreT, IouT>(rows, anchors, off + base + r, cls, key.score(), anchor, bx, sx, sy);
+            }
+            base += k;
+        }
+        return;
+    }
+
+    // truncation to top_k (ssd_output_decoder.py:219-221) or layer mode: order all kept boxes by
+    // (score desc, class asc, anchor asc) and emit the first `cnt`.
+    const int N = pow2_ceil((int)T);
+    Key128* sk = (N <= EMIT_SMEM_KEYS) ? reinterpret_cast<Key128*>(smem_raw)
+                                       : merge_scratch + (size_t)b * merge_stride;
+    // segment prefix (NS may exceed the block size: computed serially by thread 0 in chunks)
+    long long base = 0;
+    for (int s = 0; s < NS; ++s) {
+        const int k = kept_count[(size_t)b * NS + s];
+        const KeyT* kp = keys + ((size_t)b * NS + s) * g.A;
+        for (int r = threadIdx.x; r < k; r += EMIT_THREADS) {
+            KeyT key = kp[r];
+            uint32_t anchor = key.anchor();
+            int cls = (NS > 1) ? (s + 1) : cls_of[anchor];
+            Key128 ck;
+            ck.hi = key.score_bits();
+            ck.lo = ((uint64_t)(0xffffffffu - (uint32_t)cls) << 32) | (uint64_t)(0xffffffffu - anchor);
+            sk[base + r] = ck;
+        }
+        base += k;
+    }
+    for (int i = (int)T + threadIdx.x; i < N; i += EMIT_THREADS) sk[i] = Key128::lowest();
+    __syncthreads();
+    block_bitonic_sort(sk, N, false);
+    for (int r = threadIdx.x; r < cnt; r += EMIT_THREADS) {
+        Key128 ck = sk[r];
+        int cls = (int)(0xffffffffu - (uint32_t)(ck.lo >> 32));
+        uint32_t anchor = 0xffffffffu - (uint32_t)ck.lo;
+        write_row<StoreT, IouT>(rows, anchors, off + r, cls, score_from_bits<KeyT>(ck.hi), anchor, bx, sx, sy);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static float float_round_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+}
+static float float_round_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+struct IntLayout {
+    size_t seg_count, kept_count, lists, counters, total_ints;
+};
+static IntLayout int_layout(size_t nseg) {
+    IntLayout L;
+    L.counters = 0;                       // 32 ints, zeroed together with seg_count
+    L.seg_count = 32;
+    L.kept_count = L.seg_count + nseg;
+    L.lists = L.kept_count + nseg;
+    L.total_ints = L.lists + (size_t)NBINS * nseg;
+    return L;
+}
+
+template <typename InT, typename IouT, bool TF>
+static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B,
+                        double conf_thresh, int cmp_f32_rn) {
+    typedef typename KeyOf<InT>::type KeyT;
+    const bool fast = (g.NS == 1);
+    const size_t nseg = (size_t)g.nseg;
+    IntLayout L = int_layout(nseg);
+    int* ints = d->ints.as<int>();
+    int* counters = ints + L.counters;
+    int* seg_count = ints + L.seg_count;
+    int* kept_count = ints + L.kept_count;
+    int* lists = ints + L.lists;
+    KeyT* keys = d->keys.as<KeyT>();
+    SBox<InT>* boxes = d->boxes.as<SBox<InT>>();
+    int* aux = fast ? d->aux_class.as<int>() : nullptr;
+    cudaStream_t st = d->stream;
+
+    // typed threshold (hard part 1): the reference compares float64(conf) with
+    // the Python float for the centroid / minmax paths and float32 with float32(thr) for 'corners'
+    // and the Keras layers.  For float32 inputs the float64 comparison is folded into an
+    // equivalent float32 one: x > t  <=>  x > round_down_f32(t);  x >= t  <=>  x >= round_up_f32(t).
+    InT thr;
+    if (sizeof(InT) == 4) {
+        if (cmp_f32_rn) thr = (InT)(float)conf_thresh;
+        else thr = (InT)(g.ge ? float_round_up(conf_thresh) : float_round_down(conf_thresh));
+    } else {
+        thr = (InT)conf_thresh;
+    }
+
+    SSDC_CUDA(cudaMemsetAsync(ints, 0, (L.kept_count) * sizeof(int), st));
+    const int n1 = SORT_BYTES1 / (int)sizeof(KeyT), n2 = SORT_BYTES2 / (int)sizeof(KeyT), n3 = SORT_BYTES3 / (int)sizeof(KeyT);
+
+    // D1
+    {
+        constexpr int V = 16 / (int)sizeof(InT);
+        size_t tile_bytes = (((size_t)g.tile_rows * g.W + V) * sizeof(InT) + 15) & ~(size_t)15;
+        size_t smem = tile_bytes + sizeof(int) * ((size_t)2 * g.NS + (size_t)(D1_THREADS / 32) * g.NS);
+        dim3 grid((unsigned)((size_t)B * g.tiles));
+        LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
+        if (fast) {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_kernel<InT, true><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+        } else {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_kernel<InT, false><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+        }
+        SSDC_TRY(check_launch("decode_filter_kernel"));
+    }
+    // plan
+    {
+        LaunchScope ls(ctx, d, SSDC_K_PLAN);
+        plan_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(seg_count, (int)nseg, kept_count, lists, counters, n1, n2, n3);
+        SSDC_TRY(check_launch("plan_kernel"));
+    }
+    // D2: one persistent launch per size bin
+    {
+        const int sms = d->sm_count;
+        struct BinCfg { int nmax, threads, ctas_per_sm; };
+        const BinCfg cfg[4] = {{n1, 128, 8}, {n2, 512, 3}, {n3, 1024, 1}, {0, 1024, 1}};
+        for (int k = 1; k <= 4; ++k) {
+            const BinCfg& c = cfg[k - 1];
+            if (k < 4 && (size_t)g.A <= (size_t)(k == 1 ? 32 : cfg[k - 2].nmax)) continue;   // bin cannot occur
+            if (k == 4 && g.A <= n3) continue;
+            LaunchScope ls(ctx, d, SSDC_K_SORT);
+            if (k < 4) {
+                size_t smem = (size_t)c.nmax * sizeof(KeyT);
+                SSDC_CUDA(cudaFuncSetAttribute(sort_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BYTES3));
+                int ctas = (int)((227 * 1024) / (smem + 1024));
+                if (ctas > c.ctas_per_sm) ctas = c.ctas_per_sm;
+                if (ctas < 1) ctas = 1;
+                sort_kernel<KeyT, true><<<sms * ctas, c.threads, smem, st>>>(keys, seg_count, lists + (size_t)k * nseg, counters, k, g, nullptr, 0);
+            } else {
+                int stride = 1; while (stride < g.A) stride <<= 1;
+                int grid = sms;
+                if ((size_t)grid > nseg) grid = (int)nseg;
+                SSDC_TRY(d->sort_scratch.ensure((size_t)grid * stride * sizeof(KeyT)));
+                sort_kernel<KeyT, false><<<grid, c.threads, 0, st>>>(keys, seg_count, lists + (size_t)k * nseg, counters, k, g, d->sort_scratch.as<KeyT>(), stride);
+            }
+            SSDC_TRY(check_launch("sort_kernel"));
+        }
+    }
+    // D3
+    {
+        int KS = 256;
+        if (g.Kseg > 0 && g.Kseg < KS) KS = (g.Kseg + 31) & ~31;
+        size_t smem = (size_t)NMS_WARPS * (KS + 32) * sizeof(Box<IouT>);
+        int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
+        if (ctas_per_sm > 12) ctas_per_sm = 12;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        size_t want = (nseg + NMS_WARPS - 1) / NMS_WARPS;
+        size_t grid = (size_t)d->sm_count * ctas_per_sm;
+        if (grid > want) grid = want;
+        if (grid < 1) grid = 1;
+        LaunchScope ls(ctx, d, SSDC_K_NMS);
+        SSDC_CUDA(cudaFuncSetAttribute(nms_kernel<InT, IouT, KeyT, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_kernel<InT, IouT, KeyT, TF><<<(unsigned)grid, NMS_WARPS * 32, smem, st>>>(
+            keys, seg_count, kept_count, lists, counters, boxes, g, KS);
+        SSDC_TRY(check_launch("nms_kernel"));
+    }
+    // D4a
+    {
+        LaunchScope ls(ctx, d, SSDC_K_MERGE);
+        count_scan_kernel<<<1, 1024, 0, st>>>(kept_count, (int)B, g.NS, g.K, d->out_count.as<int>(), d->row_offset.as<long long>());
+        SSDC_TRY(check_launch("count_scan_kernel"));
+    }
+    return SSDC_OK;
+}
+
+template <typename InT, typename IouT>
+static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
+    typedef typename KeyOf<InT>::type KeyT;
+    IntLayout L = int_layout((size_t)g.nseg);
+    int* ints = d->ints.as<int>();
+    const bool fast = (g.NS == 1);
+    // composite-key sort space: only needed when a truncating / always-sorting merge can exceed smem
+    size_t per_image_max = (g.Kseg > 0) ? (size_t)g.NS * (size_t)min(g.Kseg, g.A) : (size_t)g.NS * g.A;
+    int stride = 0;
+    bool may_sort = g.always_sort || g.K > 0;
+    if (may_sort && per_image_max > EMIT_SMEM_KEYS) {
+        size_t s = 1; while (s < per_image_max) s <<= 1;
+        stride = (int)s;
+        SSDC_TRY(d->merge_scratch.ensure((size_t)B * s * sizeof(Key128)));
+    }
+    size_t smem = (size_t)EMIT_SMEM_KEYS * sizeof(Key128);
+    LaunchScope ls(ctx, d, SSDC_K_MERGE);
+    SSDC_CUDA(cudaFuncSetAttribute(emit_kernel<InT, IouT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emit_kernel<InT, IouT, KeyT><<<(unsigned)B, EMIT_THREADS, smem, d->stream>>>(
+        d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
+        d->boxes.as<SBox<InT>>(), fast ? d->aux_class.as<int>() : nullptr, g,
+        d->merge_scratch.as<Key128>(), stride, d->out_rows.as<double>(), d->out_anchor.as<int>());
+    SSDC_TRY(check_launch("emit_kernel"));
+    return SSDC_OK;
+}
+
+static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* tf, int* cmp_rn) {
+    const ssdc_decode_params& p = job.p;
+    DecodeArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = (int)job.A; g.C = job.C; g.W = job.C + 12;
+    const bool layer = (p.mode == SSDC_MODE_LAYER || p.mode == SSDC_MODE_LAYER_FAST);
+    const bool fast = (p.mode == SSDC_MODE_FAST || p.mode == SSDC_MODE_LAYER_FAST);
+    g.NS = fast ? 1 : job.C - 1;
+    g.nseg = (int)(job.B * g.NS);
+    g.input_coords = p.input_coords;
+    g.log_wh = p.log_wh;
+    g.layer_assoc = layer ? 1 : 0;
+    g.ge = (p.mode == SSDC_MODE_FAST) ? 1 : 0;      // `>=` only in decode_detections_fast (:325)
+    g.do_nms = (fast && !layer) ? p.do_nms : 1;
+    g.K = p.top_k > 0 ? p.top_k : 0;
+    g.Kseg = layer ? p.nms_cap : g.K;
+    g.always_sort = layer ? 1 : 0;
+    g.iou_thr = p.iou_thresh;
+    g.sx = p.normalize ? p.img_w : 1.0;
+    g.sy = p.normalize ? p.img_h : 1.0;
+    g.d = (p.border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p.border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
+    // tile rows: as many whole rows as fit a comfortable shared-memory tile
+    size_t elem = (job.dtype == SSDC_F32) ? 4 : 8;
+    int rows = D1_THREADS;
+    while (rows > 32 && ((size_t)rows * g.W + 4) * elem + 4096 > 100 * 1024) rows >>= 1;
+    g.tile_rows = rows;
+    g.tiles = (int)((job.A + rows - 1) / rows);
+    // float32 input stays float32 end to end only where the reference never upcasts:
+    // input_coords == 'corners' (ssd_output_decoder.py:186-190) and the Keras layers.
+    *iou_f32 = (job.dtype == SSDC_F32) && (layer || p.input_coords == SSDC_COORDS_CORNERS);
+    *tf = layer;
+    *cmp_rn = *iou_f32;
+    *out = g;
+    return SSDC_OK;
+}
+
+int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, int on_device,
+                      int64_t b0, int64_t B, int64_t A, int C, const ssdc_decode_params* p) {
+    SSDC_CUDA(cudaSetDevice(d->device));
+    DecodeJob& job = d->job;
+    job.valid = false;
+    job.b0 = b0; job.B = B; job.A = A; job.C = C; job.dtype = dtype; job.p = *p; job.emitted = false;
+    if (B == 0) { job.valid = true; job.NS = 0; return SSDC_OK; }
+    DecodeArgs g; int iou_f32, tf, cmp_rn;
+    SSDC_TRY(build_args(job, &g, &iou_f32, &tf, &cmp_rn));
+    job.NS = g.NS; job.iou_f32 = iou_f32;
+    const size_t elem = (dtype == SSDC_F32) ? 4 : 8;
+    const size_t in_bytes = (size_t)B * A * g.W * elem;
+    const void* y_dev = y_pred;
+    if (!on_device) {
+        SSDC_TRY(d->y_in.ensure(in_bytes));
+        SSDC_CUDA(cudaMemcpyAsync(d->y_in.p, y_pred, in_bytes, cudaMemcpyHostToDevice, d->stream));
+        y_dev = d->y_in.p;
+    }
+    const size_t nseg = (size_t)g.nseg;
+    IntLayout L = int_layout(nseg);
+    SSDC_TRY(d->ints.ensure(L.total_ints * sizeof(int)));
+    SSDC_TRY(d->keys.ensure(nseg * (size_t)A * (dtype == SSDC_F32 ? sizeof(Key64) : sizeof(Key128))));
+    SSDC_TRY(d->boxes.ensure((size_t)B * A * 4 * elem));
+    if (g.NS == 1) SSDC_TRY(d->aux_class.ensure((size_t)B * A * sizeof(int)));
+    SSDC_TRY(d->out_count.ensure((size_t)B * sizeof(int)));
+    SSDC_TRY(d->row_offset.ensure((size_t)(B + 1) * sizeof(long long)));
+
+    int r;
+    if (dtype == SSDC_F32) {
+        if (!iou_f32) r = run_pipeline<float, double, false>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
+        else if (!tf) r = run_pipeline<float, float, false>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
+        else r = run_pipeline<float, float, true>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
+    } else {
+        r = run_pipeline<double, double, false>(ctx, d, (const double*)y_dev, g, B, p->conf_thresh, cmp_rn);
+    }
+    SSDC_TRY(r);
+
+    if (g.K > 0) {
+        // bounded output: rows can be emitted right away without knowing the total
+        job.out_capacity = B * (int64_t)g.K;
+        SSDC_TRY(d->out_rows.ensure((size_t)job.out_capacity * 6 * sizeof(double)));
+        SSDC_TRY(d->out_anchor.ensure((size_t)job.out_capacity * sizeof(int)));
+        if (dtype == SSDC_F32) {
+            if (!iou_f32) r = run_emit<float, double>(ctx, d, g, B);
+            else r = run_emit<float, float>(ctx, d, g, B);
+        } else r = run_emit<double, double>(ctx, d, g, B);
+        SSDC_TRY(r);
+        job.emitted = true;
+    }
+    job.valid = true;
+    return SSDC_OK;
+}
+
+// Waits for the device, returns the number of result rows of this shard.
+int decode_finish_dev(ssdc_ctx* ctx, DevCtx* d, int64_t* total_rows) {
+    (void)ctx;
+    DecodeJob& job = d->job;
+    *total_rows = 0;
+    if (!job.valid) { set_error("ssdc_decode_collect without a submitted decode"); return SSDC_ERR_STATE; }
+    if (job.B == 0) return SSDC_OK;
+    SSDC_CUDA(cudaSetDevice(d->device));
+    long long total = 0;
+    SSDC_CUDA(cudaMemcpyAsync(&total, d->row_offset.as<long long>() + job.B, sizeof(long long), cudaMemcpyDeviceToHost, d->stream));
+    SSDC_CUDA(cudaStreamSynchronize(d->stream));
+    *total_rows = total;
+    return SSDC_OK;
+}
+
+// top_k == 'all': the row buffer is sized once the total is known, then rows are emitted.
+int decode_emit_all_dev(ssdc_ctx* ctx, DevCtx* d, int64_t total_rows) {
+    DecodeJob& job = d->job;
+    if (job.emitted || job.B == 0) return SSDC_OK;
+    SSDC_CUDA(cudaSetDevice(d->device));
+    DecodeArgs g; int iou_f32, tf, cmp_rn;
+    SSDC_TRY(build_args(job, &g, &iou_f32, &tf, &cmp_rn));
+    job.out_capacity = total_rows;
+    SSDC_TRY(d->out_rows.ensure((size_t)(total_rows + 1) * 6 * sizeof(double)));
+    SSDC_TRY(d->out_anchor.ensure((size_t)(total_rows + 1) * sizeof(int)));
+    int r;
+    if (job.dtype == SSDC_F32) {
+        if (!iou_f32) r = run_emit<float, double>(ctx, d, g, job.B);
+        else r = run_emit<float, float>(ctx, d, g, job.B);
+    } else r = run_emit<double, double>(ctx, d, g, job.B);
+    SSDC_TRY(r);
+    job.emitted = true;
+    return SSDC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone greedy NMS (greedy_nms / _greedy_nms / _greedy_nms2, ssd_output_decoder.py:27-109)
+// ---------------------------------------------------------------------------
+__global__ void nms_prep_kernel(const double* __restrict__ boxes, const double* __restrict__ scores, int n,
+                                int coords, Key128* __restrict__ keys, SBox<double>* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c4[4] = {boxes[4 * i], boxes[4 * i + 1], boxes[4 * i + 2], boxes[4 * i + 3]};
+    SBox<double> b;
+    to_corners(c4, coords, &b.x0, &b.y0, &b.x1, &b.y1);
+    out[i] = b;
+    keys[i] = Key128::make(scores[i], (uint32_t)i);
+}
+
+int greedy_nms_dev(ssdc_ctx* ctx, DevCtx* d, const double* boxes, const double* scores, int64_t n,
+                   double iou_thresh, int coords, int border_pixels, int32_t* out_keep, int64_t* n_keep) {
+    SSDC_CUDA(cudaSetDevice(d->device));
+    *n_keep = 0;
+    if (n == 0) return SSDC_OK;
+    d->job.valid = false;            // shares the decode scratch: a pending decode is invalidated
+    cudaStream_t st = d->stream;
+    DecodeArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = (int)n; g.C = 2; g.W = 14; g.NS = 1; g.nseg = 1; g.do_nms = 1; g.K = 0; g.Kseg = 0;
+    g.iou_thr = iou_thresh; g.sx = 1.0; g.sy = 1.0;
+    g.d = (border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
+    IntLayout L = int_layout(1);
+    SSDC_TRY(d->ints.ensure(L.total_ints * sizeof(int)));
+    SSDC_TRY(d->keys.ensure((size_t)n * sizeof(Key128)));
+    SSDC_TRY(d->boxes.ensure((size_t)n * sizeof(SBox<double>)));
+    SSDC_TRY(d->t0buf.ensure((size_t)n * 4 * sizeof(double)));
+    SSDC_TRY(d->t1buf.ensure((size_t)n * sizeof(double)));
+    int* ints = d->ints.as<int>();
+    int* counters = ints + L.counters;
+    int* seg_count = ints + L.seg_count;
+    int* kept_count = ints + L.kept_count;
+    int* lists = ints + L.lists;
+    Key128* keys = d->keys.as<Key128>();
+    SSDC_CUDA(cudaMemcpyAsync(d->t0buf.p, boxes, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    SSDC_CUDA(cudaMemcpyAsync(d->t1buf.p, scores, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    SSDC_CUDA(cudaMemsetAsync(ints, 0, L.kept_count * sizeof(int), st));
+    const int n32 = (int)n;
+    SSDC_CUDA(cudaMemcpyAsync(seg_count, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+    const int n1 = SORT_BYTES1 / (int)sizeof(Key128), n2 = SORT_BYTES2 / (int)sizeof(Key128), n3 = SORT_BYTES3 / (int)sizeof(Key128);
+    {
+        LaunchScope ls(ctx, d, SSDC_K_THIN);
+        nms_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d->t0buf.as<double>(), d->t1buf.as<double>(), n32, coords, keys, d->boxes.as<SBox<double>>());
+        SSDC_TRY(check_launch("nms_prep_kernel"));
+    }
+    {
+        LaunchScope ls(ctx, d, SSDC_K_PLAN);
+        plan_kernel<<<1, 256, 0, st>>>(seg_count, 1, kept_count, lists, counters, n1, n2, n3);
+        SSDC_TRY(check_launch("plan_kernel"));
+    }
+    if (n > 32) {
+        LaunchScope ls(ctx, d, SSDC_K_SORT);
+        int bin = n > n3 ? 4 : (n > n2 ? 3 : (n > n1 ? 2 : 1));
+        if (bin < 4) {
+            size_t smem = (size_t)(bin == 1 ? SORT_BYTES1 : (bin == 2 ? SORT_BYTES2 : SORT_BYTES3));
+            SSDC_CUDA(cudaFuncSetAttribute(sort_kernel<Key128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_BYTES3));
+            sort_kernel<Key128, true><<<1, bin == 1 ? 128 : (bin == 2 ? 512 : 1024), smem, st>>>(keys, seg_count, lists + (size_t)bin, counters, bin, g, nullptr, 0);
+        } else {
+            int stride = 1; while (stride < g.A) stride <<= 1;
+            SSDC_TRY(d->sort_scratch.ensure((size_t)stride * sizeof(Key128)));
+            sort_kernel<Key128, false><<<1, 1024, 0, st>>>(keys, seg_count, lists + (size_t)bin, counters, bin, g, d->sort_scratch.as<Key128>(), stride);
+        }
+        SSDC_TRY(check_launch("sort_kernel"));
+    }
+    {
+        const int KS = 256;
+        size_t smem = (size_t)NMS_WARPS * (KS + 32) * sizeof(Box<double>);
+        LaunchScope ls(ctx, d, SSDC_K_NMS);
+        SSDC_CUDA(cudaFuncSetAttribute(nms_kernel<double, double, Key128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_kernel<double, double, Key128, false><<<1, NMS_WARPS * 32, smem, st>>>(keys, seg_count, kept_count, lists, counters, d->boxes.as<SBox<double>>(), g, KS);
+        SSDC_TRY(check_launch("nms_kernel"));
+    }
+    int kept = 0;
+    SSDC_CUDA(cudaMemcpyAsync(&kept, kept_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SSDC_CUDA(cudaStreamSynchronize(st));
+    std::vector<Key128> hk((size_t)kept);
+    if (kept > 0) {
+        SSDC_CUDA(cudaMemcpyAsync(hk.data(), keys, (size_t)kept * sizeof(Key128), cudaMemcpyDeviceToHost, st));
+        SSDC_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int i = 0; i < kept; ++i) out_keep[i] = (int32_t)hk[i].anchor();
+    *n_keep = kept;
+    return SSDC_OK;
+}
+
+}  // namespace ssdc
+
+extern "C" int ssdc_greedy_nms(ssdc_ctx* ctx, const double* boxes, const double* scores, int64_t n,
+                               double iou_thresh, int coords, int border_pixels,
+                               int32_t* out_keep, int64_t* n_keep) {
+    using namespace ssdc;
+    if (!ctx || n < 0 || !n_keep || (n > 0 && (!boxes || !scores || !out_keep)) || coords < 0 || coords > 2 ||
+        border_pixels < 0 || border_pixels > 2 || n > 0x7fffffff) {
+        set_error("ssdc_greedy_nms: bad argument");
+        return SSDC_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return greedy_nms_dev(ctx, &ctx->devs[0], boxes, scores, n, iou_thresh, coords, border_pixels, out_keep, n_keep);
+}

@@ -1,0 +1,622 @@
+// encode.cu - ground truth -> training target encoding of the SSD box codec (sm_100a).
+//
+// Replaces the numpy body of
+//   SSDInputEncoder.__call__        /root/reference/localisation_part/ssd_encoder_decoder/ssd_input_encoder.py:277-418
+//   generate_encoding_template      .../ssd_input_encoder.py:550-611
+//   match_bipartite_greedy          .../matching_utils.py:22-79
+//   match_multi                     .../matching_utils.py:81-116
+//   iou (outer product)             /root/reference/localisation_part/bounding_box_utils/bounding_box_utils.py:283-383
+//
+// Kernels:
+//   anchor_prep_kernel : once per encoder: anchor corners + union area term, and the 12-double tail
+//                        [offsets | anchor | variances] every unmatched row carries (literal formula,
+//                        so 0/0 anchors still produce the reference's NaN).
+//   gt_prep_kernel     : per ground-truth row: normalise, convert to the target coordinate format,
+//                        corner form for the IoU.
+//   E1 rowbest_kernel  : per (image, anchor chunk): IoU of every GT row with the chunk's anchors,
+//                        np.argmax-faithful (value, first index) reduction per GT row.
+//   E2 match_kernel    : one warp per image: reduces the chunk partials and runs the m greedy rounds
+//                        of match_bipartite_greedy literally (including the all-zero re-match quirk);
+//                        a row is rescanned only when its best column was taken.
+//   E3 write_kernel    : per (image, anchor tile): per-anchor best GT (match_multi), neutral test,
+//                        target offsets; the tile of y_encoded is generated element by element and
+//                        streamed out with fully coalesced stores.  The encoding template is never
+//                        materialised separately.
+#include "common.cuh"
+#include "ctx.cuh"
+#include <math.h>
+#include <algorithm>
+
+struct ssdc_encoder {
+    ssdc_ctx* ctx = nullptr;
+    int64_t A = 0;
+    ssdc_encode_params p;
+    double variances[4];
+    int64_t bad_image = -1;
+    // per device of the context
+    struct PerDev { ssdc::Buf anchor_box, anchor_tail; };
+    std::vector<PerDev> dev;
+};
+
+namespace ssdc {
+
+constexpr int E1_THREADS = 256;
+constexpr int E1_PER_THREAD = 4;
+constexpr int E1_CHUNK = E1_THREADS * E1_PER_THREAD;
+constexpr int E3_THREADS = 128;
+constexpr int E3_ROWS = 128;
+
+struct GtPrep {
+    double data[4];     // target coordinates in the encoder's `coords` format (written to y_encoded)
+    Box<double> box;    // corner form + union area term, as `iou` sees it
+    int cls;
+    int pad;
+};
+
+struct EncArgs {
+    int A, C, W, coords, background_id, multi, log_wh, chunks;
+    double pos_thr, neg_thr, d;
+    double img_h, img_w;
+    int normalize;
+};
+
+// np.argmax-faithful "is (v, i) a better argmax than (bv, bi)": larger value wins, NaN beats
+// everything, equal values (or two NaNs) resolve to the lower index.
+__device__ __forceinline__ bool better(double v, int i, double bv, int bi) {
+    const bool vn = v != v, bn = bv != bv;
+    if (vn != bn) return vn;
+    if (!vn && v != bv) return v > bv;
+    return i < bi;
+}
+
+// target offsets of coordinates `t` relative to anchor `a` (ssd_input_encoder.py:396-410)
+__device__ __forceinline__ void encode_offsets(const double* t, const double* a, const double* v,
+                                               int coords, int log_wh, double* o) {
+    if (coords == SSDC_COORDS_CENTROIDS) {
+        o[0] = (t[0] - a[0]) / (a[2] * v[0]);
+        o[1] = (t[1] - a[1]) / (a[3] * v[1]);
+        double rw = t[2] / a[2], rh = t[3] / a[3];
+        if (log_wh) {
+            rw = (rw == 1.0) ? 0.0 : log(rw);
+            rh = (rh == 1.0) ? 0.0 : log(rh);
+        }
+        o[2] = rw / v[2];
+        o[3] = rh / v[3];
+    } else if (coords == SSDC_COORDS_CORNERS) {
+        double w = a[2] - a[0], h = a[3] - a[1];
+        o[0] = (t[0] - a[0]) / w / v[0];
+        o[1] = (t[1] - a[1]) / h / v[1];
+        o[2] = (t[2] - a[2]) / w / v[2];
+        o[3] = (t[3] - a[3]) / h / v[3];
+    } else {
+        double w = a[1] - a[0], h = a[3] - a[2];
+        o[0] = (t[0] - a[0]) / w / v[0];
+        o[1] = (t[1] - a[1]) / w / v[1];
+        o[2] = (t[2] - a[2]) / h / v[2];
+        o[3] = (t[3] - a[3]) / h / v[3];
+    }
+}
+
+__global__ void anchor_prep_kernel(const double* __restrict__ anchors, int A, int coords, double d, int log_wh,
+                                   double v0, double v1, double v2, double v3,
+                                   Box<double>* __restrict__ abox, double* __restrict__ tail) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    double c4[4] = {anchors[4 * a], anchors[4 * a + 1], anchors[4 * a + 2], anchors[4 * a + 3]};
+    double x0, y0, x1, y1;
+    to_corners(c4, coords, &x0, &y0, &x1, &y1);
+    abox[a] = make_box<double>(x0, y0, x1, y1, d);
+    double v[4] = {v0, v1, v2, v3};
+    double o[4];
+    encode_offsets(c4, c4, v, coords, log_wh, o);      // an unmatched row encodes the anchor against itself
+    double* t = tail + (size_t)a * 12;
+    t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
+    t[4] = c4[0]; t[5] = c4[1]; t[6] = c4[2]; t[7] = c4[3];
+    t[8] = v0; t[9] = v1; t[10] = v2; t[11] = v3;
+}
+
+__global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, GtPrep* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = gt + (size_t)i * 5;
+    double xmin = r[1], ymin = r[2], xmax = r[3], ymax = r[4];
+    if (g.normalize) {          // ssd_input_encoder.py:339-341
+        ymin = ymin / g.img_h; ymax = ymax / g.img_h;
+        xmin = xmin / g.img_w; xmax = xmax / g.img_w;
+    }
+    GtPrep p;
+    if (g.coords == SSDC_COORDS_CENTROIDS) {          // :345 -> bounding_box_utils.py:72-75
+        p.data[0] = (xmin + xmax) / 2.0;
+        p.data[1] = (ymin + ymax) / 2.0;
+        p.data[2] = xmax - xmin + g.d;
+        p.data[3] = ymax - ymin + g.d;
+    } else if (g.coords == SSDC_COORDS_MINMAX) {      // :347
+        p.data[0] = xmin; p.data[1] = xmax; p.data[2] = ymin; p.data[3] = ymax;
+    } else {
+        p.data[0] = xmin; p.data[1] = ymin; p.data[2] = xmax; p.data[3] = ymax;
+    }
+    double x0, y0, x1, y1;
+    to_corners(p.data, g.coords, &x0, &y0, &x1, &y1);
+    p.box = make_box<double>(x0, y0, x1, y1, g.d);
+    p.cls = (int)r[0];
+    p.pad = 0;
+    out[i] = p;
+}
+
+// ---------------------------------------------------------------------------
+// E1: per GT row, best anchor inside one chunk of anchors
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(E1_THREADS)
+rowbest_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+               const Box<double>* __restrict__ abox, EncArgs g,
+               double* __restrict__ part_val, int* __restrict__ part_idx, int* __restrict__ irregular) {
+    __shared__ double s_val[E1_THREADS / 32];
+    __shared__ int s_idx[E1_THREADS / 32];
+    const int chunk = blockIdx.x % g.chunks;
+    const int b = blockIdx.x / g.chunks;
+    const long long g0 = gt_off[b], g1 = gt_off[b + 1];
+    const int m = (int)(g1 - g0);
+    if (m == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a_base = chunk * E1_CHUNK;
+
+    Box<double> ab[E1_PER_THREAD];
+    int ai[E1_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < E1_PER_THREAD; ++k) {
+        ai[k] = a_base + k * E1_THREADS + tid;
+        if (ai[k] < g.A) ab[k] = abox[ai[k]];
+    }
+    bool irr = false;
+    for (int r = 0; r < m; ++r) {
+        const Box<double> gb = gtp[g0 + r].box;
+        double bv = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < E1_PER_THREAD; ++k) {
+            if (ai[k] < g.A) {
+                double s = iou_boxes<double>(gb, ab[k]);
+                irr |= (s < 0.0);
+                if (better(s, ai[k], bv, bi)) { bv = s; bi = ai[k]; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < E1_THREADS / 32; ++w)
+                if (better(s_val[w], s_idx[w], bv, bi)) { bv = s_val[w]; bi = s_idx[w]; }
+            part_val[(size_t)(g0 + r) * g.chunks + chunk] = bv;
+            part_idx[(size_t)(g0 + r) * g.chunks + chunk] = bi;
+        }
+        __syncthreads();
+    }
+    if (__any_sync(0xffffffffu, irr) && lane == 0) atomicOr(&irregular[b], 1);
+}
+
+// ---------------------------------------------------------------------------
+// E2: greedy bipartite rounds, one warp per image
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, int B,
+             const Box<double>* __restrict__ abox, EncArgs g,
+             const double* __restrict__ part_val, const int* __restrict__ part_idx,
+             const int* __restrict__ irregular,
+             double* __restrict__ rb_val, int* __restrict__ rb_idx, int* __restrict__ taken,
+             unsigned char* __restrict__ row_done, int* __restrict__ match) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const long long g0 = gt_off[b];
+    const int m = (int)(gt_off[b + 1] - g0);
+    if (m == 0) return;
+    const bool irr = irregular[b] != 0;
+
+    // initial row argmax: reduce the chunk partials
+    for (int r = 0; r < m; ++r) {
+        double bv = -INFINITY; int bi = 0x7fffffff;
+        for (int c = lane; c < g.chunks; c += 32) {
+            double v = part_val[(size_t)(g0 + r) * g.chunks + c];
+            int i = part_idx[(size_t)(g0 + r) * g.chunks + c];
+            if (better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { rb_val[g0 + r] = bv; rb_idx[g0 + r] = bi; row_done[g0 + r] = 0; match[g0 + r] = 0; }
+    }
+    __syncwarp();
+
+    // matching_utils.py:63-77: exactly m rounds
+    for (int round = 0; round < m; ++round) {
+        // ground_truth_index = np.argmax(overlaps)
+        double bv = -INFINITY; int bg = 0x7fffffff;
+        for (int r = lane; r < m; r += 32) {
+            double v = rb_val[g0 + r];
+            if (better(v, r, bv, bg)) { bv = v; bg = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int og = __shfl_xor_sync(0xffffffffu, bg, o);
+            if (better(ov, og, bv, bg)) { bv = ov; bg = og; }
+        }
+        const int gsel = bg;
+        const int asel = rb_idx[g0 + gsel];
+        __syncwarp();
+        if (lane == 0) {
+            match[g0 + gsel] = asel;
+            rb_val[g0 + gsel] = 0.0;      // weight_matrix[ground_truth_index] = 0  -> argmax 0, weight 0
+            rb_idx[g0 + gsel] = 0;
+            row_done[g0 + gsel] = 1;
+            taken[g0 + round] = asel;     // weight_matrix[:, anchor_index] = 0
+        }
+        __syncwarp();
+        // rows whose best column was just zeroed must be rescanned
+        for (int r = 0; r < m; ++r) {
+            if (row_done[g0 + r]) continue;
+            if (!irr && rb_idx[g0 + r] != asel) continue;
+            const Box<double> gb = gtp[g0 + r].box;
+            double rv = -INFINITY; int ri = 0x7fffffff;
+            for (int a = lane; a < g.A; a += 32) {
+                double s = iou_boxes<double>(gb, abox[a]);
+                for (int t = 0; t <= round; ++t)
+                    if (taken[g0 + t] == a) s = 0.0;
+                if (better(s, a, rv, ri)) { rv = s; ri = a; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, rv, o);
+                int oi = __shfl_xor_sync(0xffffffffu, ri, o);
+                if (better(ov, oi, rv, ri)) { rv = ov; ri = oi; }
+            }
+            if (lane == 0) { rb_val[g0 + r] = rv; rb_idx[g0 + r] = ri; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E3: per-anchor matching + offsets + write-out
+// ---------------------------------------------------------------------------
+struct RowMeta {
+    double off[4];
+    int cls;        // class column set to 1, or -1 for none (neutral background)
+    int pad;
+};
+
+__global__ void __launch_bounds__(E3_THREADS)
+write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+             const Box<double>* __restrict__ abox, const double* __restrict__ tail,
+             const int* __restrict__ match, EncArgs g, int tiles,
+             double* __restrict__ y, double* __restrict__ y2, int* __restrict__ midx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RowMeta* meta = reinterpret_cast<RowMeta*>(smem_raw);               // E3_ROWS
+    Box<double>* sgt = reinterpret_cast<Box<double>*>(meta + E3_ROWS);   // up to smem_gt boxes
+    const int tile = blockIdx.x % tiles;
+    const int b = blockIdx.x / tiles;
+    const int a0 = tile * E3_ROWS;
+    const int rows = min(E3_ROWS, g.A - a0);
+    const long long g0 = gt_off[b];
+    const int m = (int)(gt_off[b + 1] - g0);
+    const int tid = threadIdx.x;
+
+    // stage the image's GT boxes and bipartite matches (dynamic smem sized for the batch's max m)
+    int* smatch = reinterpret_cast<int*>(sgt + m);
+    for (int r = tid; r < m; r += E3_THREADS) { sgt[r] = gtp[g0 + r].box; smatch[r] = match[g0 + r]; }
+    __syncthreads();
+
+    if (tid < rows) {
+        const int a = a0 + tid;
+        int gsel = -1;
+        bool neutral = false;
+        if (m > 0) {
+            const Box<double> ab = abox[a];
+            // bipartite assignment: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (last write wins)
+            int bip = -1;
+            for (int r = 0; r < m; ++r) if (smatch[r] == a) bip = r;
+            // column of the similarity matrix; a bipartite column is all zeros (ssd_input_encoder.py:366)
+            double cv = -INFINITY; int cg = 0x7fffffff;
+            if (bip >= 0) { cv = 0.0; cg = 0; }
+            else {
+                for (int r = 0; r < m; ++r) {
+                    double s = iou_boxes<double>(sgt[r], ab);
+                    if (better(s, r, cv, cg)) { cv = s; cg = r; }
+                }
+            }
+            gsel = bip;
+            bool zeroed = bip >= 0;
+            if (g.multi && (cv >= g.pos_thr)) {      // matching_utils.py:109-114, ssd_input_encoder.py:375-381
+                gsel = cg;
+                zeroed = true;
+            }
+            const double rest = zeroed ? 0.0 : cv;   // np.amax of the column after the zeroing
+            neutral = rest >= g.neg_thr;              // ssd_input_encoder.py:388-390
+        }
+        RowMeta mt;
+        const double* t = tail + (size_t)a * 12;
+        if (gsel >= 0) {
+            const GtPrep gp = gtp[g0 + gsel];
+            double an[4] = {t[4], t[5], t[6], t[7]};
+            double v[4] = {t[8], t[9], t[10], t[11]};
+            encode_offsets(gp.data, an, v, g.coords, g.log_wh, mt.off);
+            mt.cls = gp.cls;
+            if (neutral && gp.cls == g.background_id) mt.cls = -1;
+        } else {
+            mt.off[0] = t[0]; mt.off[1] = t[1]; mt.off[2] = t[2]; mt.off[3] = t[3];
+            mt.cls = neutral ? -1 : g.background_id;
+        }
+        mt.pad = 0;
+        meta[tid] = mt;
+        if (midx) midx[(size_t)b * g.A + a] = (gsel >= 0) ? gsel : (neutral ? -2 : -1);
+    }
+    __syncthreads();
+
+    // stream the tile out: element e of the tile is (row e / W, column e % W)
+    const int W = g.W, C = g.C;
+    const int n = rows * W;
+    double* out = y + ((size_t)b * g.A + a0) * W;
+    double* out2 = y2 ? y2 + ((size_t)b * g.A + a0) * W : nullptr;
+    const double* tl = tail + (size_t)a0 * 12;
+    int r = tid / W, c = tid % W;
+    const int dr = E3_THREADS / W, dc = E3_THREADS % W;
+    for (int e = tid; e < n; e += E3_THREADS) {
+        double v;
+        if (c < C) v = (c == meta[r].cls) ? 1.0 : 0.0;
+        else if (c < C + 4) v = meta[r].off[c - C];
+        else v = tl[(size_t)r * 12 + (c - C)];
+        out[e] = v;
+        if (out2) out2[e] = (c >= C && c < C + 4) ? 0.0 : v;
+        r += dr; c += dc;
+        if (c >= W) { c -= W; ++r; }
+    }
+}
+
+static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, int64_t* n_gt) {
+    const int64_t first = gt_offsets[b0], last = gt_offsets[b0 + B];
+    const int64_t n = last - first;
+    *n_gt = n;
+    SSDC_TRY(d->gt_off.ensure((size_t)(B + 1) * sizeof(long long)));
+    SSDC_TRY(d->h_small.ensure((size_t)(B + 1) * sizeof(long long)));
+    long long* h = d->h_small.as<long long>();
+    for (int64_t i = 0; i <= B; ++i) h[i] = gt_offsets[b0 + i] - first;
+    SSDC_CUDA(cudaMemcpyAsync(d->gt_off.p, h, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->stream));
+    if (n > 0) {
+        SSDC_TRY(d->gt.ensure((size_t)n * 5 * sizeof(double) + (size_t)n * sizeof(GtPrep)));
+        SSDC_CUDA(cudaMemcpyAsync(d->gt.p, gt + first * 5, (size_t)n * 5 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    }
+    return SSDC_OK;
+}
+
+int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B,
+               int max_m, double* y_dev, double* y2_dev, int* midx_dev) {
+    ssdc_ctx* ctx = enc->ctx;
+    DevCtx* d = &ctx->devs[slot];
+    SSDC_CUDA(cudaSetDevice(d->device));
+    if (B == 0) return SSDC_OK;
+    const ssdc_encode_params& p = enc->p;
+    EncArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = (int)enc->A; g.C = p.n_classes; g.W = p.n_classes + 12; g.coords = p.coords;
+    g.background_id = p.background_id; g.multi = p.matching_multi; g.log_wh = p.log_wh;
+    g.chunks = (int)((enc->A + E1_CHUNK - 1) / E1_CHUNK);
+    g.pos_thr = p.pos_iou_threshold; g.neg_thr = p.neg_iou_limit;
+    g.d = (p.border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p.border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
+    g.img_h = p.img_h; g.img_w = p.img_w; g.normalize = p.normalize;
+
+    int64_t n_gt = 0;
+    SSDC_TRY(upload_gt(d, gt, gt_offsets, b0, B, &n_gt));
+    cudaStream_t st = d->stream;
+    const long long* gt_off = d->gt_off.as<long long>();
+    const Box<double>* abox = enc->dev[slot].anchor_box.as<Box<double>>();
+    const double* tail = enc->dev[slot].anchor_tail.as<double>();
+    GtPrep* gtp = nullptr;
+    int* match = nullptr;
+    if (n_gt > 0) {
+        gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (size_t)n_gt * 5 * sizeof(double));
+        // scratch: partials (val, idx), row bests, taken columns, done flags, matches, irregular flags
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        size_t o_pv = carve((size_t)n_gt * g.chunks * sizeof(double));
+        size_t o_pi = carve((size_t)n_gt * g.chunks * sizeof(int));
+        size_t o_rv = carve((size_t)n_gt * sizeof(double));
+        size_t o_ri = carve((size_t)n_gt * sizeof(int));
+        size_t o_tk = carve((size_t)n_gt * sizeof(int));
+        size_t o_dn = carve((size_t)n_gt);
+        size_t o_mt = carve((size_t)n_gt * sizeof(int));
+        size_t o_ir = carve((size_t)B * sizeof(int));
+        SSDC_TRY(d->partial.ensure(off));
+        char* base = d->partial.as<char>();
+        double* part_val = reinterpret_cast<double*>(base + o_pv);
+        int* part_idx = reinterpret_cast<int*>(base + o_pi);
+        double* rb_val = reinterpret_cast<double*>(base + o_rv);
+        int* rb_idx = reinterpret_cast<int*>(base + o_ri);
+        int* taken = reinterpret_cast<int*>(base + o_tk);
+        unsigned char* done = reinterpret_cast<unsigned char*>(base + o_dn);
+        match = reinterpret_cast<int*>(base + o_mt);
+        int* irregular = reinterpret_cast<int*>(base + o_ir);
+        SSDC_CUDA(cudaMemsetAsync(irregular, 0, (size_t)B * sizeof(int), st));
+        {
+            LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
+            gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
+            SSDC_TRY(check_launch("gt_prep_kernel"));
+        }
+        {
+            LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
+            rowbest_kernel<<<(unsigned)(B * g.chunks), E1_THREADS, 0, st>>>(gtp, gt_off, abox, g, part_val, part_idx, irregular);
+            SSDC_TRY(check_launch("rowbest_kernel"));
+        }
+        {
+            LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
+            match_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(gtp, gt_off, (int)B, abox, g, part_val, part_idx, irregular,
+                                                                   rb_val, rb_idx, taken, done, match);
+            SSDC_TRY(check_launch("match_kernel"));
+        }
+    }
+    {
+        const int tiles = (int)((enc->A + E3_ROWS - 1) / E3_ROWS);
+        size_t smem = sizeof(RowMeta) * E3_ROWS + (size_t)max_m * (sizeof(Box<double>) + sizeof(int)) + 16;
+        LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+        SSDC_CUDA(cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        write_kernel<<<(unsigned)(B * tiles), E3_THREADS, smem, st>>>(gtp, gt_off, abox, tail, match, g, tiles, y_dev, y2_dev, midx_dev);
+        SSDC_TRY(check_launch("write_kernel"));
+    }
+    return SSDC_OK;
+}
+
+}  // namespace ssdc
+
+using namespace ssdc;
+
+extern "C" {
+
+int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const double* variances,
+                        const ssdc_encode_params* p, ssdc_encoder** out) {
+    if (!ctx || !anchors || !variances || !p || !out || A <= 0) { set_error("ssdc_encoder_create: bad argument"); return SSDC_ERR_ARG; }
+    if (p->n_classes < 1 || p->coords < 0 || p->coords > 2 || p->border_pixels < 0 || p->border_pixels > 2 ||
+        p->background_id < 0 || p->background_id >= p->n_classes) {
+        set_error("ssdc_encoder_create: bad params"); return SSDC_ERR_ARG;
+    }
+    if (A > 0x7fffffff / (p->n_classes + 12)) { set_error("ssdc_encoder_create: too many anchors"); return SSDC_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ssdc_encoder* enc = new ssdc_encoder();
+    enc->ctx = ctx; enc->A = A; enc->p = *p;
+    for (int i = 0; i < 4; ++i) enc->variances[i] = variances[i];
+    enc->dev.resize(ctx->devs.size());
+    const double dd = (p->border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p->border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
+    for (size_t i = 0; i < ctx->devs.size(); ++i) {
+        DevCtx& d = ctx->devs[i];
+        int r = SSDC_OK;
+        if (cudaSetDevice(d.device) != cudaSuccess) r = SSDC_ERR_CUDA;
+        if (r == SSDC_OK) r = enc->dev[i].anchor_box.ensure((size_t)A * sizeof(Box<double>));
+        if (r == SSDC_OK) r = enc->dev[i].anchor_tail.ensure((size_t)A * 12 * sizeof(double));
+        if (r == SSDC_OK) r = d.t0buf.ensure((size_t)A * 4 * sizeof(double));
+        if (r == SSDC_OK && cudaMemcpyAsync(d.t0buf.p, anchors, (size_t)A * 4 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) r = SSDC_ERR_CUDA;
+        if (r == SSDC_OK) {
+            LaunchScope ls(ctx, &d, SSDC_K_THIN);
+            anchor_prep_kernel<<<(unsigned)((A + 127) / 128), 128, 0, d.stream>>>(
+                d.t0buf.as<double>(), (int)A, p->coords, dd, p->log_wh, variances[0], variances[1], variances[2], variances[3],
+                enc->dev[i].anchor_box.as<Box<double>>(), enc->dev[i].anchor_tail.as<double>());
+            r = check_launch("anchor_prep_kernel");
+        }
+        if (r == SSDC_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) { set_error("anchor_prep failed: %s", cudaGetErrorString(cudaGetLastError())); r = SSDC_ERR_CUDA; }
+        if (r != SSDC_OK) {
+            for (auto& pd : enc->dev) { pd.anchor_box.release(); pd.anchor_tail.release(); }
+            delete enc;
+            return r;
+        }
+    }
+    *out = enc;
+    return SSDC_OK;
+}
+
+void ssdc_encoder_destroy(ssdc_encoder* enc) {
+    if (!enc) return;
+    std::lock_guard<std::mutex> lk(enc->ctx->mu);
+    for (size_t i = 0; i < enc->dev.size(); ++i) {
+        cudaSetDevice(enc->ctx->devs[i].device);
+        enc->dev[i].anchor_box.release();
+        enc->dev[i].anchor_tail.release();
+    }
+    delete enc;
+}
+
+int64_t ssdc_encoder_bad_image(const ssdc_encoder* enc) { return enc ? enc->bad_image : -1; }
+
+int ssdc_encode(ssdc_encoder* enc, const double* gt, const int64_t* gt_offsets, int64_t B,
+                int on_device, double* y_encoded, double* y_matched, int32_t* match_idx) {
+    if (!enc || !gt_offsets || B < 0 || (B > 0 && !y_encoded)) { set_error("ssdc_encode: bad argument"); return SSDC_ERR_ARG; }
+    ssdc_ctx* ctx = enc->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    enc->bad_image = -1;
+    const int64_t n_total = gt_offsets[B] - gt_offsets[0];
+    if (n_total > 0 && !gt) { set_error("ssdc_encode: gt is NULL"); return SSDC_ERR_ARG; }
+    // host-side validation (ssd_input_encoder.py:333-336 and the class index used at :349)
+    int max_m = 0;
+    for (int64_t i = 0; i < B; ++i) {
+        const int64_t m = gt_offsets[i + 1] - gt_offsets[i];
+        if (m < 0) { set_error("ssdc_encode: gt_offsets must be non-decreasing"); return SSDC_ERR_ARG; }
+        if (m > max_m) max_m = (int)m;
+        for (int64_t r = gt_offsets[i]; r < gt_offsets[i + 1]; ++r) {
+            const double* row = gt + r * 5;
+            if (row[3] - row[1] <= 0 || row[4] - row[2] <= 0) {
+                enc->bad_image = i;
+                set_error("degenerate ground truth box in batch item %lld", (long long)i);
+                return SSDC_ERR_DEGENERATE;
+            }
+            if (!(row[0] > -1.0 && row[0] < (double)enc->p.n_classes)) {
+                enc->bad_image = i;
+                set_error("class id %g of batch item %lld out of range [0, %d)", row[0], (long long)i, enc->p.n_classes);
+                return SSDC_ERR_ARG;
+            }
+        }
+    }
+    if ((size_t)max_m * (sizeof(Box<double>) + sizeof(int)) > 160 * 1024) {
+        set_error("ssdc_encode: more than %d ground-truth boxes in one image are not supported", (int)(160 * 1024 / 44));
+        return SSDC_ERR_ARG;
+    }
+    const int n = (int)ctx->devs.size();
+    const size_t img_elems = (size_t)enc->A * (enc->p.n_classes + 12);
+    if (on_device) {
+        if (n != 1) { set_error("ssdc_encode: device-resident output needs a single-device context"); return SSDC_ERR_ARG; }
+        return encode_dev(enc, 0, gt, gt_offsets, 0, B, max_m, y_encoded, y_matched, match_idx);
+    }
+    for (int i = 0; i < n; ++i) {
+        DevCtx& d = ctx->devs[i];
+        int64_t per = (B + n - 1) / n;
+        int64_t b0 = std::min<int64_t>(B, per * i), b1 = std::min<int64_t>(B, per * (i + 1));
+        if (b1 == b0) continue;
+        SSDC_CUDA(cudaSetDevice(d.device));
+        SSDC_TRY(d.enc_out.ensure((size_t)(b1 - b0) * img_elems * sizeof(double)));
+        if (y_matched) SSDC_TRY(d.enc_out2.ensure((size_t)(b1 - b0) * img_elems * sizeof(double)));
+        if (match_idx) SSDC_TRY(d.enc_idx.ensure((size_t)(b1 - b0) * enc->A * sizeof(int)));
+        SSDC_TRY(encode_dev(enc, i, gt, gt_offsets, b0, b1 - b0, max_m, d.enc_out.as<double>(),
+                            y_matched ? d.enc_out2.as<double>() : nullptr, match_idx ? d.enc_idx.as<int>() : nullptr));
+        SSDC_CUDA(cudaMemcpyAsync(y_encoded + (size_t)b0 * img_elems, d.enc_out.p, (size_t)(b1 - b0) * img_elems * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        if (y_matched)
+            SSDC_CUDA(cudaMemcpyAsync(y_matched + (size_t)b0 * img_elems, d.enc_out2.p, (size_t)(b1 - b0) * img_elems * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        if (match_idx)
+            SSDC_CUDA(cudaMemcpyAsync(match_idx + (size_t)b0 * enc->A, d.enc_idx.p, (size_t)(b1 - b0) * enc->A * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (DevCtx& d : ctx->devs) {
+        SSDC_CUDA(cudaSetDevice(d.device));
+        SSDC_CUDA(cudaStreamSynchronize(d.stream));
+    }
+    return SSDC_OK;
+}
+
+int ssdc_encoding_template(ssdc_encoder* enc, int64_t B, double* out) {
+    // generate_encoding_template (ssd_input_encoder.py:550-611): all-zero class vector, anchors in
+    // both coordinate slots, variances.  Host-side tiling of construction-time data is not on the
+    // hot path (the encode kernels never materialise it); it is produced from the device tail table
+    // to keep a single source of truth.
+    if (!enc || B < 0 || (B > 0 && !out)) { set_error("ssdc_encoding_template: bad argument"); return SSDC_ERR_ARG; }
+    ssdc_ctx* ctx = enc->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevCtx& d = ctx->devs[0];
+    SSDC_CUDA(cudaSetDevice(d.device));
+    const int C = enc->p.n_classes, W = C + 12;
+    std::vector<double> tail((size_t)enc->A * 12);
+    SSDC_CUDA(cudaMemcpyAsync(tail.data(), enc->dev[0].anchor_tail.p, tail.size() * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+    SSDC_CUDA(cudaStreamSynchronize(d.stream));
+    for (int64_t b = 0; b < B; ++b) {
+        for (int64_t a = 0; a < enc->A; ++a) {
+            double* row = out + ((size_t)b * enc->A + a) * W;
+            for (int c = 0; c < C; ++c) row[c] = 0.0;
+            const double* t = tail.data() + (size_t)a * 12;
+            for (int k = 0; k < 4; ++k) { row[C + k] = t[4 + k]; row[C + 4 + k] = t[4 + k]; row[C + 8 + k] = t[8 + k]; }
+        }
+    }
+    return SSDC_OK;
+}
+
+}  // extern "C"

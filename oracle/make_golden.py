@@ -1,0 +1,175 @@
+"""Generates tests/golden/*.npz by running the REAL reference (from /root/reference) and the
+oracle restatement on the same seeded inputs, requiring bit-identical outputs (this is what
+pins the oracle), and stores the reference outputs in a compact canonical form.
+
+    python oracle/make_golden.py            # only works where /root/reference exists
+
+Test infrastructure; never imported by the product.
+"""
+from __future__ import division
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import cases, ref_loader                      # noqa: E402
+from oracle import ssd_codec_oracle as orc                # noqa: E402
+from jpeg_detection_resnet_ssd_b200 import synth          # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+EXP_PROBE = np.linspace(-3.0, 3.0, 4001).astype(np.float32)
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+
+
+def golden_decode(ref, case):
+    y = cases.build_decode_input(case, ref.encoder.SSDInputEncoder)
+    log_wh = case.get('log_wh', True)
+    mod = ref.decoder if log_wh else ref.decoder_no_log
+    kw = dict(case['kwargs'])
+    t = time.time()
+    r = getattr(mod, case['fn'])(y, **kw)
+    t_ref = time.time() - t
+    ofn = getattr(orc, case['fn'])
+    o = ofn(y, log_wh=log_wh, exp_mode='numpy', **kw)
+    assert len(r) == len(o)
+    for a, b in zip(r, o):
+        assert same(a, b), 'oracle != reference for ' + case['name']
+    oa = ofn(y, log_wh=log_wh, exp_mode='numpy', with_anchor_index=True, **kw)
+    oc = ofn(y, log_wh=log_wh, exp_mode='cr', with_anchor_index=True, **kw)
+    for a, b in zip(r, oa):
+        assert np.size(a) == np.size(b) == 0 or same(a, np.asarray(b)[:, :6].astype(a.dtype)), case['name']
+    if case['fn'] == 'decode_detections' and all(np.size(a) for a in r) and kw.get('top_k') != 'all' and log_wh:
+        # anchor ids straight from the reference's own debug decoder
+        dbg = ref.decoder.decode_detections_debug(y, **kw)
+        for a, b in zip(dbg, oa):
+            b = np.asarray(b)
+            # (the debug decoder associates (off * size) * var, so its coordinates may differ by an
+            # ulp from decode_detections'; box id, class and confidence must agree exactly)
+            assert same(a[:, :3], np.concatenate([b[:, 6:7], b[:, :2]], axis=1)), 'debug anchors differ ' + case['name']
+
+    def canon(per_image):
+        moved = []
+        for p in per_image:
+            if np.size(p) == 0:
+                moved.append(np.zeros((0, 7)))
+            else:
+                p = np.asarray(p, dtype=np.float64)
+                moved.append(np.concatenate([p[:, 6:7], p[:, :6]], axis=1))
+        return cases.canonical_rows(moved)
+
+    rows, counts = canon(oa)
+    rows_cr, counts_cr = canon(oc)
+    out_dtype = str(np.asarray(r[0]).dtype) if len(r) else 'float64'
+    empty_shapes = json.dumps([list(np.asarray(a).shape) for a in r])
+    np.savez_compressed(os.path.join(GOLDEN, case['name'] + '.npz'),
+                        input_sha=cases.sha256_of(y), rows=rows, counts=counts, rows_cr=rows_cr,
+                        counts_cr=counts_cr, out_dtype=out_dtype, shapes=empty_shapes,
+                        case=json.dumps({k: v for k, v in case.items()}))
+    print('%-26s ref %.2fs  rows %d  cr-identical %s' % (case['name'], t_ref, rows.shape[0],
+                                                        same(rows, rows_cr)))
+
+
+def golden_encode(ref, case):
+    gt = cases.build_encode_input(case)
+    kw = synth.layout_kwargs(case['layout'], **case.get('overrides', {}))
+    log_wh = case.get('log_wh', True)
+    rmod = ref.encoder if log_wh else ref.encoder_no_log
+    renc = rmod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(log_wh=log_wh, **kw)
+    assert same(synth.anchors_of(renc), synth.anchors_of(oenc))
+    diag = case.get('diagnostics', False)
+    t = time.time()
+    with np.errstate(all='ignore'):
+        rr = renc(gt, diagnostics=diag)
+        t_ref = time.time() - t
+        oo = oenc(gt, diagnostics=diag, return_matches=True)
+    y_ref = rr[0] if diag else rr
+    y_orc, mi = oo[0], oo[-1]
+    assert same(y_ref, y_orc), 'oracle != reference for ' + case['name']
+    if diag:
+        assert same(rr[1], oo[1])
+    B, A, W = y_ref.shape
+    flat_mi = mi.reshape(-1)
+    nz = np.nonzero(flat_mi != -1)[0]
+    np.savez_compressed(os.path.join(GOLDEN, case['name'] + '.npz'),
+                        input_sha=cases.sha256_of(*gt) if len(gt) else '', y_sha=cases.sha256_of(y_ref),
+                        shape=np.array([B, A, W]), nz_idx=nz.astype(np.int64), nz_match=flat_mi[nz],
+                        nz_rows=y_ref.reshape(B * A, W)[nz], template_sha=cases.sha256_of(renc.generate_encoding_template(2)),
+                        case=json.dumps({k: v for k, v in case.items()}))
+    print('%-26s ref %.2fs  matched %d neutral %d' % (case['name'], t_ref, (flat_mi >= 0).sum(), (flat_mi == -2).sum()))
+
+
+def golden_thin(ref):
+    inp = cases.thin_inputs()
+    out = dict(inp)
+    for fmt in ('corners', 'minmax', 'centroids'):
+        for border in ('half', 'include', 'exclude'):
+            r = ref.bbox.iou(inp['b1_' + fmt], inp['b2_' + fmt], coords=fmt, mode='outer_product', border_pixels=border)
+            o = orc.iou(inp['b1_' + fmt], inp['b2_' + fmt], coords=fmt, mode='outer_product', border_pixels=border)
+            assert same(r, o)
+            out['iou_outer_%s_%s' % (fmt, border)] = r
+            r = ref.bbox.iou(inp['b1_' + fmt], inp['b3_' + fmt], coords=fmt, mode='element-wise', border_pixels=border)
+            o = orc.iou(inp['b1_' + fmt], inp['b3_' + fmt], coords=fmt, mode='element-wise', border_pixels=border)
+            assert same(r, o)
+            out['iou_elem_%s_%s' % (fmt, border)] = r
+            r = ref.bbox.iou(inp['b1_' + fmt], inp['b2_' + fmt][0], coords=fmt, mode='element-wise', border_pixels=border)
+            out['iou_bcast_%s_%s' % (fmt, border)] = r
+            if fmt != 'centroids':
+                out['inter_outer_%s_%s' % (fmt, border)] = ref.bbox.intersection_area(
+                    inp['b1_' + fmt], inp['b2_' + fmt], coords=fmt, mode='outer_product', border_pixels=border)
+    for conv in ('minmax2centroids', 'centroids2minmax', 'corners2centroids', 'centroids2corners',
+                 'minmax2corners', 'corners2minmax'):
+        for border in ('half', 'include', 'exclude'):
+            for key, start in (('conv32', 3), ('conv64', -5)):
+                r = ref.bbox.convert_coordinates(inp[key], start_index=start, conversion=conv, border_pixels=border)
+                o = orc.convert_coordinates(inp[key], start_index=start, conversion=conv, border_pixels=border)
+                assert same(r, o)
+                out['conv_%s_%s_%s' % (key, conv, border)] = r
+    for key in ('w_small', 'w_quirk'):
+        r = ref.matching.match_bipartite_greedy(inp[key])
+        assert same(np.asarray(r), np.asarray(orc.match_bipartite_greedy(inp[key])))
+        out['bip_' + key] = np.asarray(r, dtype=np.int64)
+        g, a = ref.matching.match_multi(inp[key], 0.5)
+        go, ao = orc.match_multi(inp[key], 0.5)
+        assert same(np.asarray(g), np.asarray(go)) and same(np.asarray(a), np.asarray(ao))
+        out['multi_gt_' + key] = np.asarray(g, dtype=np.int64)
+        out['multi_anchor_' + key] = np.asarray(a, dtype=np.int64)
+    rows = inp['nms_rows']
+    r = ref.decoder.greedy_nms([rows, rows[:40]], iou_threshold=0.3, coords='corners', border_pixels='half')
+    o = orc.greedy_nms([rows, rows[:40]], iou_threshold=0.3, coords='corners', border_pixels='half')
+    assert all(same(a, b) for a, b in zip(r, o))
+    out['nms_full'] = r[0]
+    out['nms_40'] = r[1]
+    out['nms1'] = ref.decoder._greedy_nms(rows[:, 1:], iou_threshold=0.45, coords='corners', border_pixels='include')
+    out['nms2'] = ref.decoder._greedy_nms2(rows, iou_threshold=0.45, coords='corners', border_pixels='half')
+    np.savez_compressed(os.path.join(GOLDEN, 'thin_ops.npz'), **out)
+    print('thin ops: %d arrays' % len(out))
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ref_loader.load()
+    only = sys.argv[1:]
+    np.savez_compressed(os.path.join(GOLDEN, 'exp_probe.npz'), x=EXP_PROBE, y=np.exp(EXP_PROBE))
+    for case in cases.DECODE_CASES:
+        if not only or case['name'] in only:
+            golden_decode(ref, case)
+    for case in cases.ENCODE_CASES:
+        if not only or case['name'] in only:
+            golden_encode(ref, case)
+    if not only or 'thin' in only:
+        golden_thin(ref)
+
+
+if __name__ == '__main__':
+    main()

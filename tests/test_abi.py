@@ -1,0 +1,122 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, exports every symbol the header
+declares, and the product path fails loudly (no CPU fallback) when no device is usable."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'ssdcodec.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(ssdc_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), s
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == syms          # the ctypes table binds exactly the header
+    assert _lib.load_library().ssdc_version() >= 100
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(['cuobjdump', '--list-elf', built_lib], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    assert not re.search(r'sm_(?!100a)\d+', out)
+
+
+def test_struct_layouts_match_header():
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    assert ctypes.sizeof(_lib.DecodeParams) == 8 * 4 + 4 * 8
+    assert ctypes.sizeof(_lib.EncodeParams) == 8 * 4 + 4 * 8
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the product path must raise, never compute on the host."""
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    lib = _lib.load_library()
+    if lib.ssdc_device_count() > 0:
+        pytest.skip('a GPU is visible here')
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_output_decoder import decode_detections
+    from jpeg_detection_resnet_ssd_b200.bounding_box_utils.bounding_box_utils import iou
+    y = np.zeros((1, 10, 16), np.float32)
+    with pytest.raises(_lib.SSDCodecError) as e:
+        decode_detections(y, img_height=10, img_width=10)
+    assert e.value.code == _lib.ERR_NODEVICE
+    with pytest.raises(_lib.SSDCodecError):
+        iou(np.zeros((1, 4)), np.zeros((1, 4)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                assert 'import torch' not in text, f
+
+
+def test_argument_validation_before_device():
+    """Errors the reference raises from pure argument checks keep type and text."""
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_output_decoder import decode_detections, decode_detections_fast
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    from jpeg_detection_resnet_ssd_b200.keras_layers.keras_layer_DecodeDetections import DecodeDetections
+    y = np.zeros((1, 10, 16), np.float32)
+    with pytest.raises(ValueError, match='needs the image size'):
+        decode_detections(y)
+    with pytest.raises(ValueError, match='needs the image size'):
+        decode_detections_fast(y, img_height=3)
+    with pytest.raises(ValueError, match='Supported input coordinate formats'):
+        decode_detections(y, input_coords='xywh', img_height=1, img_width=1)
+    with pytest.raises(ValueError, match="only supports the 'centroids'"):
+        DecodeDetections(coords='minmax', img_height=1, img_width=1)
+    ok = dict(img_height=300, img_width=300, n_classes=20, predictor_sizes=[(4, 4), (2, 2)])
+    with pytest.raises(ValueError, match='len\\(scales\\)'):
+        SSDInputEncoder(scales=[0.1, 0.2], **ok)
+    with pytest.raises(ValueError, match='greater than 0'):
+        SSDInputEncoder(scales=[0.1, -0.2, 0.3], **ok)
+    with pytest.raises(ValueError, match='min_scale <= max_scale'):
+        SSDInputEncoder(min_scale=0.9, max_scale=0.1, **ok)
+    with pytest.raises(ValueError, match='aspect_ratios_per_layer'):
+        SSDInputEncoder(aspect_ratios_per_layer=[[1.0]], **ok)
+    with pytest.raises(ValueError, match='aspect ratios must be greater'):
+        SSDInputEncoder(aspect_ratios_global=[1.0, -2.0], **ok)
+    with pytest.raises(ValueError, match='4 variance values'):
+        SSDInputEncoder(variances=[0.1, 0.2], **ok)
+    with pytest.raises(ValueError, match='variances must be >0'):
+        SSDInputEncoder(variances=[0.1, 0.1, 0.0, 0.2], **ok)
+    with pytest.raises(ValueError, match='Unexpected value for `coords`'):
+        SSDInputEncoder(coords='polar', **ok)
+    with pytest.raises(ValueError, match='one step value'):
+        SSDInputEncoder(steps=[8], **ok)
+    with pytest.raises(ValueError, match='one offset value'):
+        SSDInputEncoder(offsets=[0.5], **ok)
+
+
+def test_anchor_generation_matches_oracle():
+    """Construction-time host configuration: product anchors == oracle anchors, bit for bit."""
+    from oracle import ssd_codec_oracle as orc
+    from jpeg_detection_resnet_ssd_b200 import synth
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    for layout, n in (('ssd300', 8732), ('ssd512', 24564), ('tiny', None)):
+        for over in (dict(), dict(coords='corners'), dict(coords='minmax'), dict(clip_boxes=True), dict(normalize_coords=False)):
+            a = synth.anchors_of(synth.make_encoder(SSDInputEncoder, layout, **over))
+            b = synth.anchors_of(synth.make_encoder(orc.SSDInputEncoder, layout, **over))
+            assert np.array_equal(a, b)
+            if n:
+                assert a.shape == (n, 4)
+    e = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    a = synth.anchors_of(e)
+    assert np.allclose(a[0], [0.013333, 0.013333, 0.1, 0.1], atol=1e-6)
+    assert np.allclose(a[-1], [0.5, 0.5, 0.622254, 1.244508], atol=1e-6)
+    assert e.n_boxes == [4, 6, 6, 6, 4, 4] and e.n_classes == 21

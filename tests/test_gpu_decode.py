@@ -1,0 +1,199 @@
+"""GPU parity tests of the decode + NMS path, through the C ABI (ctypes), against the committed
+golden vectors of the real reference and against the oracle run live on fresh seeds."""
+import numpy as np
+import pytest
+
+from oracle import cases
+from oracle import ssd_codec_oracle as orc
+from jpeg_detection_resnet_ssd_b200 import _lib, synth
+from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder as dec
+from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder_no_log as dec_nolog
+from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+
+from helpers import load_golden, product_rows7, to_rows7, rel_err
+
+pytestmark = pytest.mark.gpu
+
+COORD_RTOL = 1e-5     # north_star: box coordinates within 1e-5 relative in float32
+
+
+def run_product(case, y, ctx):
+    kw = dict(case['kwargs'])
+    mode = _lib.MODE_PER_CLASS if case['fn'] == 'decode_detections' else _lib.MODE_FAST
+    iou_thr = kw.get('iou_threshold')
+    do_nms = True if mode == _lib.MODE_PER_CLASS else bool(iou_thr)
+    return _lib.run_decode(y, mode, kw['confidence_thresh'], iou_thr if do_nms else 0.0, kw['top_k'],
+                           kw['input_coords'], kw['normalize_coords'], kw.get('img_height'), kw.get('img_width'),
+                           kw.get('border_pixels', 'half'), log_wh=case.get('log_wh', True), do_nms=do_nms, ctx=ctx)
+
+
+def compare_rows(got, got_counts, want, want_counts, exact_coords):
+    assert np.array_equal(got_counts, want_counts), (got_counts, want_counts)
+    # kept-box anchor indices, classes and confidences: bit-exact
+    assert np.array_equal(got[:, :3], want[:, :3])
+    err = rel_err(got[:, 3:], want[:, 3:])
+    assert err.max(initial=0.0) <= COORD_RTOL
+    if exact_coords:
+        assert np.array_equal(got[:, 3:], want[:, 3:])
+
+
+@pytest.mark.parametrize('case', cases.DECODE_CASES, ids=lambda c: c['name'])
+def test_decode_matches_golden(case, ctx):
+    g = load_golden(case['name'])
+    y = cases.build_decode_input(case, SSDInputEncoder)
+    if cases.sha256_of(y) != str(g['input_sha']):
+        if case.get('roundtrip'):
+            pytest.skip('round-trip input depends on device log(); covered by test_roundtrip_live')
+        pytest.skip('this host regenerates a different synthetic input (RNG / libm drift)')
+    rows, counts, idx = run_product(case, y, ctx)
+    got, got_counts = product_rows7(rows, counts, idx)
+    # (1) against the reference run with a correctly rounded float32 exp: everything bit-exact
+    compare_rows(got, got_counts, g['rows_cr'], g['counts_cr'], exact_coords=True)
+    # (2) against the reference exactly as numpy executed it on the generating host (float32
+    #     np.exp is up to 2 ulp off): indices bit-exact, coordinates within tolerance
+    compare_rows(got, got_counts, g['rows'], g['counts'], exact_coords=False)
+
+
+@pytest.mark.parametrize('case', cases.DECODE_CASES, ids=lambda c: c['name'])
+def test_public_api_matches_golden(case, ctx):
+    """Through the reference-named Python functions (list-of-arrays contract, shapes, dtypes)."""
+    g = load_golden(case['name'])
+    y = cases.build_decode_input(case, SSDInputEncoder)
+    if cases.sha256_of(y) != str(g['input_sha']):
+        pytest.skip('input drift')
+    mod = dec if case.get('log_wh', True) else dec_nolog
+    out = getattr(mod, case['fn'])(y, **case['kwargs'])
+    import json
+    shapes = json.loads(str(g['shapes']))
+    assert [list(np.asarray(o).shape) for o in out] == shapes
+    assert all(str(np.asarray(o).dtype) == str(g['out_dtype']) for o in out if np.size(o))
+    # rows in reference order when nothing was truncated: class ascending, score descending
+    want = g['rows_cr']
+    pos = 0
+    for o, c in zip(out, g['counts_cr']):
+        c = int(c)
+        if c == 0:
+            continue
+        w = want[pos:pos + c, 1:]
+        pos += c
+        o = np.asarray(o, dtype=np.float64)
+        order = np.lexsort((-o[:, 1], o[:, 0]))
+        assert np.array_equal(o[order][:, :2], w[np.lexsort((-w[:, 1], w[:, 0]))][:, :2])
+
+
+@pytest.mark.parametrize('seed', [21, 22])
+@pytest.mark.parametrize('bias,hot', [(9.0, 40), (6.5, 40)])
+def test_decode_vs_live_oracle_ssd300(seed, bias, hot, ctx):
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 2, seed, bg_bias=bias, hot=hot)
+    kw = dict(confidence_thresh=0.01, iou_threshold=0.45, top_k=200, input_coords='centroids',
+              normalize_coords=True, img_height=300, img_width=300)
+    want, want_counts = to_rows7(orc.decode_detections(y, exp_mode='cr', with_anchor_index=True, **kw))
+    rows, counts, idx = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half', ctx=ctx)
+    got, got_counts = product_rows7(rows, counts, idx)
+    compare_rows(got, got_counts, want, want_counts, exact_coords=True)
+
+
+def test_decode_ssd512_dense_low_threshold(ctx):
+    """BASELINE config 4 in miniature: SSD512 layout, conf 0.001, dense candidates (huge segments:
+    exercises the large shared-memory and global-memory sort bins)."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd512')
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 1, 31, bg_bias=6.0, hot=40)
+    kw = dict(confidence_thresh=0.001, iou_threshold=0.45, top_k=200, input_coords='centroids',
+              normalize_coords=True, img_height=512, img_width=512)
+    want, want_counts = to_rows7(orc.decode_detections(y, exp_mode='cr', with_anchor_index=True, **kw))
+    rows, counts, idx = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.001, 0.45, 200, 'centroids', True, 512, 512, 'half', ctx=ctx)
+    got, got_counts = product_rows7(rows, counts, idx)
+    compare_rows(got, got_counts, want, want_counts, exact_coords=True)
+
+
+def test_roundtrip_live(ctx):
+    """encode -> decode_detections_fast round trip (BASELINE config 5 in miniature): every positive
+    confidence is exactly 1.0, so every NMS decision is a tie broken by anchor index."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    oenc = synth.make_encoder(orc.SSDInputEncoder, 'ssd300')
+    gt = synth.synth_ground_truth(300, 300, 20, 6, 41)
+    y = enc(gt)
+    kw = dict(confidence_thresh=0.5, iou_threshold=0.45, top_k='all', input_coords='centroids',
+              normalize_coords=True, img_height=300, img_width=300)
+    want, want_counts = to_rows7(orc.decode_detections_fast(y, with_anchor_index=True, **kw))
+    rows, counts, idx = _lib.run_decode(y, _lib.MODE_FAST, 0.5, 0.45, 'all', 'centroids', True, 300, 300, 'half', ctx=ctx)
+    got, got_counts = product_rows7(rows, counts, idx)
+    compare_rows(got, got_counts, want, want_counts, exact_coords=False)
+    # and the decoded boxes reproduce the ground truth they were encoded from
+    for b, g in enumerate(gt):
+        r = got[int(np.sum(got_counts[:b])):int(np.sum(got_counts[:b + 1]))]
+        for row in r:
+            d = np.abs(g[:, 1:5] - row[3:7]).max(axis=1)
+            k = int(np.argmin(d))
+            assert d[k] < 1e-6 and g[k, 0] == row[1]
+
+
+def test_properties_full_batch(ctx):
+    """Size-independent properties at a batch the oracle could not finish: B = 256 SSD300 images.
+    (a) per image at most top_k rows, classes in 1..20, confidences > threshold and equal to the
+    input tensor's value at (anchor, class); (b) inside a class scores are non-increasing and no two
+    kept boxes overlap by more than the IoU threshold (NMS fixed point); (c) decoding the same
+    image twice inside one batch gives identical rows (batch independence); (d) idempotence."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    B = 256
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, B // 2, 51, bg_bias=7.0, hot=40)
+    y = np.concatenate([y, y], axis=0)
+    rows, counts, idx = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half', ctx=ctx)
+    assert counts.shape == (B,) and counts.max() <= 200 and counts.sum() == rows.shape[0]
+    off = np.concatenate([[0], np.cumsum(counts)])
+    assert np.array_equal(counts[:B // 2], counts[B // 2:])
+    assert np.array_equal(rows[:off[B // 2]], rows[off[B // 2]:])
+    cls = rows[:, 0].astype(int)
+    assert cls.min() >= 1 and cls.max() <= 20 and np.all(rows[:, 1] > 0.01)
+    img = np.repeat(np.arange(B), counts)
+    assert np.array_equal(rows[:, 1], y[img, idx, cls].astype(np.float64))
+    for b in range(0, B // 2, 17):
+        r = rows[off[b]:off[b + 1]]
+        for c in np.unique(r[:, 0]):
+            rc = r[r[:, 0] == c]
+            if counts[b] < 200:
+                assert np.all(np.diff(rc[:, 1]) <= 0)
+            if rc.shape[0] > 1:
+                m = orc.iou(rc[:, 2:], rc[:, 2:], coords='corners', mode='outer_product')
+                np.fill_diagonal(m, 0)
+                assert m.max() <= 0.45
+    rows2, counts2, idx2 = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half', ctx=ctx)
+    assert np.array_equal(rows, rows2) and np.array_equal(counts, counts2) and np.array_equal(idx, idx2)
+
+
+def test_edge_cases(ctx):
+    enc = synth.make_encoder(SSDInputEncoder, 'tiny')
+    anchors = synth.anchors_of(enc)
+    # batch of zero images, and an image without a single candidate
+    y0 = np.zeros((0, anchors.shape[0], 16), np.float32)
+    assert dec.decode_detections(y0, img_height=96, img_width=128) == []
+    y = synth.synth_y_pred(anchors, enc.variances, 4, 2, 61, bg_bias=30.0, hot=0)
+    out = dec.decode_detections(y, img_height=96, img_width=128)
+    assert [o.shape for o in out] == [(0,), (0,)]
+    out = dec.decode_detections_fast(y, img_height=96, img_width=128)
+    assert [o.shape for o in out] == [(0,), (0,)]
+    # NaN confidences never pass the threshold; NaN boxes are suppressed by any kept box
+    y = synth.synth_y_pred(anchors, enc.variances, 4, 1, 62, bg_bias=1.0, hot=5)
+    y[0, ::7, 1] = np.nan
+    w = orc.decode_detections(y, 0.05, 0.45, 200, 'centroids', True, 96, 128, exp_mode='cr')
+    p = dec.decode_detections(y, 0.05, 0.45, 200, 'centroids', True, 96, 128)
+    assert np.array_equal(np.asarray(w[0])[:, :2], p[0][:, :2])
+    # argument errors surface as the reference's exceptions
+    with pytest.raises(ValueError):
+        dec.decode_detections(y)
+    with pytest.raises(ValueError):
+        dec.decode_detections(y, input_coords='polar', img_height=1, img_width=1)
+
+
+def test_debug_decoder_and_layers(ctx):
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 2, 71, bg_bias=8.0, hot=50)
+    a = dec.decode_detections(y, 0.01, 0.45, 200, 'centroids', True, 300, 300)
+    d = dec.decode_detections_debug(y, 0.01, 0.45, 200, 'centroids', True, 300, 300)
+    assert all(np.array_equal(x, z[:, 1:]) for x, z in zip(a, d))
+    sizes = [(38, 38), (19, 19), (10, 10), (5, 5), (3, 3), (1, 1)]
+    nb = dec.get_num_boxes_per_pred_layer(sizes, synth.LAYOUTS['ssd300']['aspect_ratios_per_layer'], True)
+    assert sum(nb) == 8732
+    layers = dec.get_pred_layers(d, nb)
+    assert all(0 <= l < 6 for ls in layers for l in ls)

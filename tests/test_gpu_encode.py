@@ -1,0 +1,104 @@
+"""GPU parity tests of SSDInputEncoder (matching + offset encoding) through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import cases
+from oracle import ssd_codec_oracle as orc
+from jpeg_detection_resnet_ssd_b200 import synth
+from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_input_encoder as enc_mod
+from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_input_encoder_no_log as enc_nolog
+
+from helpers import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+OFFSET_RTOL = 1e-5    # north_star: encoded offsets within 1e-5 relative
+
+
+def make(case):
+    kw = synth.layout_kwargs(case['layout'], **case.get('overrides', {}))
+    mod = enc_mod if case.get('log_wh', True) else enc_nolog
+    return mod.SSDInputEncoder(**kw), kw
+
+
+@pytest.mark.parametrize('case', cases.ENCODE_CASES, ids=lambda c: c['name'])
+def test_encode_matches_golden(case, ctx):
+    g = load_golden(case['name'])
+    gt = cases.build_encode_input(case)
+    assert (cases.sha256_of(*gt) if len(gt) else '') == str(g['input_sha'])
+    enc, kw = make(case)
+    out = enc(gt, diagnostics=case.get('diagnostics', False), return_matches=True)
+    y, mi = out[0], out[-1]
+    B, A, W = y.shape
+    assert [B, A, W] == list(g['shape'])
+    flat = mi.reshape(-1)
+    nz = np.nonzero(flat != -1)[0]
+    # matched-anchor assignments and neutral set: bit-exact
+    assert np.array_equal(nz, g['nz_idx'])
+    assert np.array_equal(flat[nz], g['nz_match'])
+    got = y.reshape(B * A, W)[nz]
+    C = W - 12
+    assert np.array_equal(got[:, :C], g['nz_rows'][:, :C])                    # class vectors
+    assert np.array_equal(got[:, C + 4:], g['nz_rows'][:, C + 4:])            # anchors + variances
+    assert rel_err(got[:, C:C + 4], g['nz_rows'][:, C:C + 4]).max(initial=0.0) <= OFFSET_RTOL
+    # every other row is the plain background row of the template
+    rest = np.ones(B * A, dtype=bool)
+    rest[nz] = False
+    bg = y.reshape(B * A, W)[rest]
+    expect = np.zeros(C)
+    expect[kw.get('background_id', 0)] = 1
+    assert np.array_equal(bg[:, :C], np.broadcast_to(expect, bg[:, :C].shape))
+    assert np.all(bg[:, C:C + 4] == 0)
+    anchors = np.tile(synth.anchors_of(enc), (B, 1))[rest]
+    assert np.array_equal(bg[:, C + 4:C + 8], anchors)
+    assert np.array_equal(bg[:, C + 8:], np.broadcast_to(np.asarray(kw['variances'], dtype=float), bg[:, C + 8:].shape))
+    if case.get('diagnostics'):
+        y2 = out[1]
+        assert np.all(y2[:, :, C:C + 4] == 0)
+        assert np.array_equal(np.delete(y2, np.s_[C:C + 4], axis=2), np.delete(y, np.s_[C:C + 4], axis=2))
+
+
+@pytest.mark.parametrize('seed', [81, 82, 83])
+def test_encode_vs_live_oracle(seed, ctx):
+    kw = synth.layout_kwargs('ssd300', neg_iou_limit=0.3)
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    gt = synth.synth_ground_truth(300, 300, 20, 8, seed, max_boxes=25)
+    y, mi = enc(gt, return_matches=True)
+    yo, mo = oenc(gt, return_matches=True)
+    assert np.array_equal(mi, mo)
+    assert rel_err(y, yo).max() <= OFFSET_RTOL
+    C = 21
+    assert np.array_equal(y[:, :, :C], yo[:, :, :C]) and np.array_equal(y[:, :, C + 4:], yo[:, :, C + 4:])
+
+
+def test_template_and_errors(ctx):
+    kw = synth.layout_kwargs('tiny')
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    assert np.array_equal(enc.generate_encoding_template(3), oenc.generate_encoding_template(3))
+    t, centers, wh, steps, offs = enc.generate_encoding_template(1, diagnostics=True)
+    assert len(centers) == 3 and len(wh) == 3
+    bad = [np.array([[1, 10, 10, 10, 30]], dtype=float)]
+    with pytest.raises(enc_mod.DegenerateBoxError):
+        enc([np.array([[1, 5, 5, 50, 50]], dtype=float)] + bad)
+    with pytest.raises(IndexError):
+        enc([np.array([[9, 5, 5, 50, 50]], dtype=float)])
+    # batch of empty images: pure background
+    y = enc([np.zeros((0, 5)), np.zeros((0, 5))])
+    assert np.all(y[:, :, 0] == 1) and np.all(y[:, :, 1:8] == 0)
+
+
+def test_encode_many_boxes_and_large_batch(ctx):
+    """more ground-truth boxes than any VOC image has, and a batch large enough to need several
+    waves: compared with the oracle on a sample of images, checked for batch independence."""
+    kw = synth.layout_kwargs('ssd300')
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    gt = synth.synth_ground_truth(300, 300, 20, 64, 91, max_boxes=60, min_boxes=30)
+    gt = gt + gt
+    y, mi = enc(gt, return_matches=True)
+    assert np.array_equal(y[:64], y[64:]) and np.array_equal(mi[:64], mi[64:])
+    yo, mo = oenc(gt[:4], return_matches=True)
+    assert np.array_equal(mi[:4], mo)
+    assert rel_err(y[:4], yo).max() <= OFFSET_RTOL

@@ -1,0 +1,120 @@
+"""CPU tests: the oracle restatement against the committed golden vectors (which were produced
+by the real reference, see oracle/make_golden.py) and, where /root/reference is present, against
+the live reference itself."""
+import numpy as np
+import pytest
+
+from oracle import cases, ref_loader
+from oracle import ssd_codec_oracle as orc
+from jpeg_detection_resnet_ssd_b200 import synth
+
+from helpers import load_golden, host_exp_matches_golden, to_rows7, rel_err
+
+FAST_DECODE = [c for c in cases.DECODE_CASES if c['name'] not in ('d_ssd300_ties',)]
+
+
+@pytest.mark.parametrize('case', cases.DECODE_CASES, ids=lambda c: c['name'])
+def test_decode_oracle_matches_golden(case):
+    g = load_golden(case['name'])
+    y = cases.build_decode_input(case, orc.SSDInputEncoder)
+    if cases.sha256_of(y) != str(g['input_sha']):
+        pytest.skip('this host regenerates a different synthetic input (RNG / libm drift)')
+    fn = getattr(orc, case['fn'])
+    out = fn(y, log_wh=case.get('log_wh', True), exp_mode='numpy', with_anchor_index=True, **case['kwargs'])
+    rows, counts = to_rows7(out)
+    assert np.array_equal(counts, g['counts'])
+    exp_free = case.get('gen', {}).get('exp_free') or not case.get('log_wh', True)
+    if host_exp_matches_golden() or exp_free:
+        assert np.array_equal(rows, g['rows'])            # bit-exact restatement of the reference
+    else:                                                  # other host CPU: np.exp differs by ulps
+        assert np.array_equal(rows[:, :3], g['rows'][:, :3])
+        assert rel_err(rows[:, 3:], g['rows'][:, 3:]).max() <= 1e-5
+    # the correctly rounded exp variant (what the CUDA kernels implement)
+    out = fn(y, log_wh=case.get('log_wh', True), exp_mode='cr', with_anchor_index=True, **case['kwargs'])
+    rows, counts = to_rows7(out)
+    assert np.array_equal(counts, g['counts_cr'])
+    assert np.array_equal(rows[:, :3], g['rows_cr'][:, :3])
+    assert rel_err(rows[:, 3:], g['rows_cr'][:, 3:]).max() <= 1e-6
+
+
+@pytest.mark.parametrize('case', cases.ENCODE_CASES, ids=lambda c: c['name'])
+def test_encode_oracle_matches_golden(case):
+    g = load_golden(case['name'])
+    gt = cases.build_encode_input(case)
+    kw = synth.layout_kwargs(case['layout'], **case.get('overrides', {}))
+    enc = orc.SSDInputEncoder(log_wh=case.get('log_wh', True), **kw)
+    with np.errstate(all='ignore'):
+        out = enc(gt, diagnostics=case.get('diagnostics', False), return_matches=True)
+    y, mi = out[0], out[-1]
+    B, A, W = y.shape
+    assert [B, A, W] == list(g['shape'])
+    flat = mi.reshape(-1)
+    nz = np.nonzero(flat != -1)[0]
+    assert np.array_equal(nz, g['nz_idx'])
+    assert np.array_equal(flat[nz], g['nz_match'])
+    got = y.reshape(B * A, W)[nz]
+    # np.log is the only non-IEEE-exact step; everything else must be bit-identical
+    assert rel_err(got, g['nz_rows']).max() <= 1e-12
+    if cases.sha256_of(y) == str(g['y_sha']):
+        return
+    # background rows: [one-hot background | 0 0 0 0 | anchor | variances]
+    rest = np.ones(B * A, dtype=bool)
+    rest[nz] = False
+    bg = y.reshape(B * A, W)[rest]
+    C = W - 12
+    expect = np.zeros(C)
+    expect[kw.get('background_id', 0)] = 1
+    assert np.array_equal(bg[:, :C], np.tile(expect, (bg.shape[0], 1)))
+    assert np.all(bg[:, C:C + 4] == 0)
+
+
+def test_thin_ops_oracle_matches_golden():
+    g = load_golden('thin_ops')
+    for fmt in ('corners', 'minmax', 'centroids'):
+        for border in ('half', 'include', 'exclude'):
+            o = orc.iou(g['b1_' + fmt], g['b2_' + fmt], coords=fmt, mode='outer_product', border_pixels=border)
+            assert np.array_equal(o, g['iou_outer_%s_%s' % (fmt, border)])
+            o = orc.iou(g['b1_' + fmt], g['b3_' + fmt], coords=fmt, mode='element-wise', border_pixels=border)
+            assert np.array_equal(o, g['iou_elem_%s_%s' % (fmt, border)])
+    for key in ('w_small', 'w_quirk'):
+        assert np.array_equal(orc.match_bipartite_greedy(g[key]), g['bip_' + key])
+        gt, an = orc.match_multi(g[key], 0.5)
+        assert np.array_equal(gt, g['multi_gt_' + key]) and np.array_equal(an, g['multi_anchor_' + key])
+    rows = g['nms_rows']
+    o = orc.greedy_nms([rows, rows[:40]], iou_threshold=0.3, coords='corners', border_pixels='half')
+    assert np.array_equal(o[0], g['nms_full']) and np.array_equal(o[1], g['nms_40'])
+
+
+def test_bipartite_rematch_quirk_is_in_golden():
+    """matching_utils.py:63-77 runs m rounds even when nothing is left to match: an all-zero row
+    re-assigns the lowest such row to column 0 (SURVEY section 7, quirk list)."""
+    g = load_golden('thin_ops')
+    m = g['bip_w_quirk']
+    assert m[2] == 0 and len(m) == 6
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='/root/reference not present on this host')
+@pytest.mark.parametrize('seed', [11, 12, 13])
+def test_oracle_vs_live_reference_random(seed):
+    """Fresh seeds (not in the golden set): the restatement and the real reference must agree bit
+    for bit on decode, fast decode, encode and the round trip."""
+    ref = ref_loader.load()
+    kw = synth.layout_kwargs('tiny')
+    renc = ref.encoder.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    anchors = synth.anchors_of(renc)
+    assert np.array_equal(anchors, synth.anchors_of(oenc))
+    y = synth.synth_y_pred(anchors, renc.variances, 4, 3, seed, bg_bias=1.5, hot=12)
+    for top_k in (6, 'all'):
+        r = ref.decoder.decode_detections(y, 0.05, 0.4, top_k, 'centroids', True, 96, 128)
+        o = orc.decode_detections(y, 0.05, 0.4, top_k, 'centroids', True, 96, 128)
+        assert all(np.array_equal(a, b) for a, b in zip(r, o))
+    r = ref.decoder.decode_detections_fast(y, 0.3, 0.45, 'all', 'centroids', True, 96, 128)
+    o = orc.decode_detections_fast(y, 0.3, 0.45, 'all', 'centroids', True, 96, 128)
+    assert all(np.array_equal(a, b) for a, b in zip(r, o))
+    gt = synth.synth_ground_truth(96, 128, 3, 6, seed)
+    yr, yo = renc(gt), oenc(gt)
+    assert np.array_equal(yr, yo)
+    r = ref.decoder.decode_detections_fast(yr, 0.5, 0.45, 'all', 'centroids', True, 96, 128)
+    o = orc.decode_detections_fast(yo, 0.5, 0.45, 'all', 'centroids', True, 96, 128)
+    assert all(np.array_equal(a, b) for a, b in zip(r, o))
