@@ -10,7 +10,7 @@ from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decode
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder_no_log as dec_nolog
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
 
-from helpers import load_golden, product_rows7, to_rows7, rel_err
+from helpers import load_golden, product_rows7, to_rows7, rel_err, explain_index_mismatches
 
 pytestmark = pytest.mark.gpu
 
@@ -31,8 +31,10 @@ def compare_rows(got, got_counts, want, want_counts, exact_coords):
     assert np.array_equal(got_counts, want_counts), (got_counts, want_counts)
     # kept-box anchor indices, classes and confidences: bit-exact
     assert np.array_equal(got[:, :3], want[:, :3])
-    err = rel_err(got[:, 3:], want[:, 3:])
-    assert err.max(initial=0.0) <= COORD_RTOL
+    # relative to the coordinate, with a floor of one pixel for coordinates near zero (xmin = cx - w/2
+    # cancels, so a pure relative error is ill-posed at the image border)
+    diff = np.abs(got[:, 3:] - want[:, 3:])
+    assert np.all(diff <= COORD_RTOL * np.maximum(np.abs(want[:, 3:]), 1.0))
     if exact_coords:
         assert np.array_equal(got[:, 3:], want[:, 3:])
 
@@ -48,10 +50,22 @@ def test_decode_matches_golden(case, ctx):
     rows, counts, idx = run_product(case, y, ctx)
     got, got_counts = product_rows7(rows, counts, idx)
     # (1) against the reference run with a correctly rounded float32 exp: everything bit-exact
-    compare_rows(got, got_counts, g['rows_cr'], g['counts_cr'], exact_coords=True)
+    # (for float64 inputs exp() itself is only faithful to <= 1 ulp on either side)
+    compare_rows(got, got_counts, g['rows_cr'], g['counts_cr'], exact_coords=(y.dtype == np.float32))
     # (2) against the reference exactly as numpy executed it on the generating host (float32
-    #     np.exp is up to 2 ulp off): indices bit-exact, coordinates within tolerance
-    compare_rows(got, got_counts, g['rows'], g['counts'], exact_coords=False)
+    #     np.exp is up to 2 ulp off): indices bit-exact, coordinates within tolerance - unless the
+    #     reference's own result depends on the exp implementation, in which case every divergence
+    #     must be proven threshold-ambiguous
+    same = (np.array_equal(got_counts, g['counts']) and np.array_equal(got[:, :3], g['rows'][:, :3]))
+    if same:
+        compare_rows(got, got_counts, g['rows'], g['counts'], exact_coords=False)
+    else:
+        assert not np.array_equal(g['rows'][:, :3], g['rows_cr'][:, :3]) or not np.array_equal(g['counts'], g['counts_cr'])
+        kw = case['kwargs']
+        n = explain_index_mismatches(got, got_counts, g['rows'], g['counts'], kw['iou_threshold'],
+                                     border=kw.get('border_pixels', 'half'),
+                                     agnostic=(case['fn'] == 'decode_detections_fast'), top_k=kw['top_k'])
+        assert n > 0
 
 
 @pytest.mark.parametrize('case', cases.DECODE_CASES, ids=lambda c: c['name'])
@@ -178,7 +192,10 @@ def test_edge_cases(ctx):
     y[0, ::7, 1] = np.nan
     w = orc.decode_detections(y, 0.05, 0.45, 200, 'centroids', True, 96, 128, exp_mode='cr')
     p = dec.decode_detections(y, 0.05, 0.45, 200, 'centroids', True, 96, 128)
-    assert np.array_equal(np.asarray(w[0])[:, :2], p[0][:, :2])
+    w0 = np.asarray(w[0])
+    w0 = w0[np.lexsort((w0[:, 2], -w0[:, 1], w0[:, 0]))]
+    p0 = p[0][np.lexsort((p[0][:, 2], -p[0][:, 1], p[0][:, 0]))]
+    assert np.array_equal(w0, p0)
     # argument errors surface as the reference's exceptions
     with pytest.raises(ValueError):
         dec.decode_detections(y)

@@ -48,7 +48,11 @@ def test_encode_matches_golden(case, ctx):
     expect = np.zeros(C)
     expect[kw.get('background_id', 0)] = 1
     assert np.array_equal(bg[:, :C], np.broadcast_to(expect, bg[:, :C].shape))
-    assert np.all(bg[:, C:C + 4] == 0)
+    if case.get('log_wh', True):
+        assert np.all(bg[:, C:C + 4] == 0)
+    else:    # *_no_log twin: an unmatched row encodes (w_a / w_a) / variance
+        v = np.asarray(kw['variances'], dtype=float)
+        assert np.all(bg[:, C:C + 2] == 0) and np.array_equal(bg[:, C + 2:C + 4], np.broadcast_to(1.0 / v[2:], bg[:, C + 2:C + 4].shape))
     anchors = np.tile(synth.anchors_of(enc), (B, 1))[rest]
     assert np.array_equal(bg[:, C + 4:C + 8], anchors)
     assert np.array_equal(bg[:, C + 8:], np.broadcast_to(np.asarray(kw['variances'], dtype=float), bg[:, C + 8:].shape))
