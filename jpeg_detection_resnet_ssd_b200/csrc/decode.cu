@@ -81,28 +81,98 @@ __device__ __forceinline__ SBox<InT> decode_box(const InT* row, int C, const Dec
     return b;
 }
 
+// One tile = `rows` whole rows of y_pred staged in shared memory at `dst` (row stride W).  Thread t
+// owns row t: it builds the bit mask of its classes that pass the confidence threshold, the warp
+// aggregates the per-class counts with ballots, ONE warp-wide atomicAdd reserves the slots of all
+// classes present in the warp (lane c reserves for class c), and the keys are written.  Warps never
+// wait for one another, so there is no block-level synchronisation inside a tile.
+template <typename InT, bool FAST>
+__device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int rows, int b, int a0,
+                                             const DecodeArgs& g, InT thr, int* __restrict__ seg_count,
+                                             typename KeyOf<InT>::type* __restrict__ keys,
+                                             SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
+    typedef typename KeyOf<InT>::type KeyT;
+    const int W = g.W, C = g.C, NS = g.NS, A = g.A;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool valid = tid < rows;
+    const InT* row = dst + (size_t)(valid ? tid : 0) * W;
+    const int a = a0 + tid;
+    const unsigned lt = (1u << lane) - 1u;
+
+    if (FAST) {
+        // ssd_output_decoder.py:292-293 (np.argmax = first maximum, NaN wins), :324-325
+        InT best = row[0];
+        bool nan = best != best;
+        int cls = 0;
+        for (int c = 1; c < C; ++c) {
+            InT v = row[c];
+            nan |= (v != v);
+            if (v > best) { best = v; cls = c; }
+        }
+        const bool pass = valid && !nan && cls != 0 && (g.ge ? (best >= thr) : (best > thr));
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&seg_count[b], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                keys[(size_t)b * A + base + __popc(m & lt)] = KeyT::make(best, (uint32_t)a);
+                aux_class[(size_t)b * A + a] = cls;
+                boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
+            }
+        }
+        return;
+    }
+
+    // ssd_output_decoder.py:207-209, 32 classes per pass
+    bool any = false;
+    for (int c0 = 0; c0 < NS; c0 += 32) {
+        const int nc = min(32, NS - c0);
+        unsigned mask = 0;
+        if (g.ge) {
+            for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] >= thr) << c;
+        } else {
+            for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] > thr) << c;
+        }
+        if (!valid) mask = 0;
+        const unsigned u = __reduce_or_sync(0xffffffffu, mask);
+        if (!u) continue;
+        any |= (mask != 0);
+        int mycnt = 0;
+        for (unsigned uu = u; uu; uu &= uu - 1) {
+            const int c = __ffs(uu) - 1;
+            const unsigned m = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+            if (lane == c) mycnt = __popc(m);
+        }
+        int mybase = 0;
+        if ((u >> lane) & 1u) mybase = atomicAdd(&seg_count[(size_t)b * NS + c0 + lane], mycnt);
+        for (unsigned uu = u; uu; uu &= uu - 1) {
+            const int c = __ffs(uu) - 1;
+            const unsigned m = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+            const int base = __shfl_sync(0xffffffffu, mybase, c);
+            if ((mask >> c) & 1u)
+                keys[((size_t)b * NS + c0 + c) * A + base + __popc(m & lt)] = KeyT::make(row[1 + c0 + c], (uint32_t)a);
+        }
+    }
+    if (any) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
+}
+
+// Fallback loader: 128-bit LDG -> STS staging of one tile per CTA (any alignment).
 template <typename InT, bool FAST>
 __global__ void __launch_bounds__(D1_THREADS)
 decode_filter_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr,
                      int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
                      SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
-    typedef typename KeyOf<InT>::type KeyT;
     constexpr int V = 16 / (int)sizeof(InT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int W = g.W, C = g.C, NS = g.NS, A = g.A;
+    const int W = g.W, A = g.A;
     InT* tile = reinterpret_cast<InT*>(smem_raw);
-    const size_t tile_bytes = (((size_t)g.tile_rows * W + V) * sizeof(InT) + 15) & ~(size_t)15;
-    int* cnt_s = reinterpret_cast<int*>(smem_raw + tile_bytes);
-    int* base_s = cnt_s + NS;
-    int* woff_s = base_s + NS;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int tile_id = blockIdx.x % g.tiles;
     const int b = blockIdx.x / g.tiles;
     const int a0 = tile_id * g.tile_rows;
     const int rows = min(g.tile_rows, A - a0);
 
-    // ---- stage the contiguous span of `rows` whole rows into shared memory ----
     const InT* src = y + ((size_t)b * A + a0) * W;
     const int n = rows * W;
     const int mis = (int)((reinterpret_cast<uintptr_t>(src) / sizeof(InT)) % V);
@@ -130,68 +200,83 @@ decode_filter_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr,
             }
         }
     }
-    for (int s = tid; s < NS; s += D1_THREADS) cnt_s[s] = 0;
+    __syncthreads();
+    process_tile<InT, FAST>(dst, rows, b, a0, g, thr, seg_count, keys, boxes, aux_class);
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar`.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Main loader: persistent CTAs, each streaming its tiles through a ring of shared-memory stages that
+// one elected thread fills with TMA bulk copies (UBLKCP) while the other warps filter the previous
+// tile.  Requires 16-byte aligned tile spans (host checks; else the LDG kernel above runs).
+constexpr int D1_STAGES = 2;
+template <typename InT, bool FAST>
+__global__ void __launch_bounds__(D1_THREADS)
+decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int total_tiles,
+                         int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
+                         SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[D1_STAGES];
+    const int W = g.W, A = g.A;
+    const size_t stage_bytes = (((size_t)g.tile_rows * W * sizeof(InT)) + 127) & ~(size_t)127;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < D1_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const bool valid = tid < rows;
-    const InT* row = dst + (size_t)(valid ? tid : 0) * W;
-    const int a = a0 + tid;
-    const unsigned lt = (1u << lane) - 1u;
-
-    bool any = false;
-    InT fbest = InT(0);
-    int fcls = 0;
-    if (FAST) {
-        // ssd_output_decoder.py:292-293 (np.argmax = first maximum, NaN wins), :324-325
-        InT best = row[0];
-        bool nan = best != best;
-        int cls = 0;
-        for (int c = 1; c < C; ++c) {
-            InT v = row[c];
-            nan |= (v != v);
-            if (v > best) { best = v; cls = c; }
-        }
-        bool pass = valid && !nan && cls != 0 && (g.ge ? (best >= thr) : (best > thr));
-        fbest = best; fcls = cls; any = pass;
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m && lane == 0) woff_s[warp] = atomicAdd(&cnt_s[0], __popc(m));
-    } else {
-        // ssd_output_decoder.py:207-209
-        for (int c = 1; c < C; ++c) {
-            InT v = row[c];
-            bool pass = valid && (g.ge ? (v >= thr) : (v > thr));
-            unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                if (lane == 0) woff_s[warp * NS + c - 1] = atomicAdd(&cnt_s[c - 1], __popc(m));
-                any |= pass;
-            }
+    auto issue = [&](int t, int s) {
+        const int b = t / g.tiles, tile_id = t - b * g.tiles;
+        const int a0 = tile_id * g.tile_rows;
+        const int rows = min(g.tile_rows, A - a0);
+        const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
+        mbar_expect_tx(&full[s], bytes);
+        tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < D1_STAGES; ++s) {
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < total_tiles) issue(t, s);
         }
     }
-    __syncthreads();
-    for (int s = tid; s < NS; s += D1_THREADS) {
-        int cnt = cnt_s[s];
-        base_s[s] = cnt ? atomicAdd(&seg_count[(size_t)b * NS + s], cnt) : 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int s = it % D1_STAGES;
+        const uint32_t parity = (uint32_t)((it / D1_STAGES) & 1);
+        mbar_wait(&full[s], parity);
+        const int b = t / g.tiles, tile_id = t - b * g.tiles;
+        const int a0 = tile_id * g.tile_rows;
+        const int rows = min(g.tile_rows, A - a0);
+        process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
+                                seg_count, keys, boxes, aux_class);
+        __syncthreads();                                   // every warp is done with stage s
+        const int tn = t + D1_STAGES * gridDim.x;
+        if (tid == 0 && tn < total_tiles) issue(tn, s);
     }
-    __syncthreads();
-    if (FAST) {
-        unsigned m = __ballot_sync(0xffffffffu, any);
-        if (any) {
-            int pos = base_s[0] + woff_s[warp] + __popc(m & lt);
-            keys[(size_t)b * A + pos] = KeyT::make(fbest, (uint32_t)a);
-            aux_class[(size_t)b * A + a] = fcls;
-        }
-    } else {
-        for (int c = 1; c < C; ++c) {
-            InT v = row[c];
-            bool pass = valid && (g.ge ? (v >= thr) : (v > thr));
-            unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (pass) {
-                int pos = base_s[c - 1] + woff_s[warp * NS + c - 1] + __popc(m & lt);
-                keys[((size_t)b * NS + c - 1) * A + pos] = KeyT::make(v, (uint32_t)a);
-            }
-        }
-    }
-    if (any) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -209,12 +294,12 @@ __device__ __forceinline__ int warp_append(int* counter, bool want) {
 }
 
 __global__ void plan_kernel(const int* __restrict__ seg_count, int nseg, int* __restrict__ kept_count,
-                            int* __restrict__ lists, int* __restrict__ counters, int n1, int n2, int n3) {
+                            int* __restrict__ lists, int* __restrict__ counters, int sort_min, int n1, int n2, int n3) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     int n = (s < nseg) ? seg_count[s] : 0;
     if (s < nseg) kept_count[s] = 0;
     int bin = 0;
-    if (n > n3) bin = 4; else if (n > n2) bin = 3; else if (n > n1) bin = 2; else if (n > 32) bin = 1;
+    if (n > n3) bin = 4; else if (n > n2) bin = 3; else if (n > n1) bin = 2; else if (n > sort_min) bin = 1;
     int pos = warp_append(&counters[CNT_LIST + 0], n > 0);
     if (n > 0) lists[pos] = s;
 #pragma unroll
@@ -264,19 +349,85 @@ __device__ __forceinline__ Box<IouT> load_box(const SBox<StoreT>* __restrict__ b
     return make_box<IouT>((IouT)s.x0 * sx, (IouT)s.y0 * sy, (IouT)s.x1 * sx, (IouT)s.y1 * sy, d);
 }
 
+// `regular`: finite coordinates and a finite positive area term.  For two regular boxes that do not
+// overlap, the reference's IoU is exactly +0 (inter = 0, union = a1 + a2 > 0), so the decision is
+// `0 <= thr` without evaluating the division.  The four comparisons imply
+// min(x1) <= max(x0) or min(y1) <= max(y0) for any boxes, i.e. a zero side length.
+template <typename T>
+__device__ __forceinline__ bool box_regular(const Box<T>& b) { return b.area > T(0) && b.area < T(INFINITY); }
+template <typename T>
+__device__ __forceinline__ bool boxes_disjoint(const Box<T>& a, const Box<T>& b) {
+    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
+}
+
+// Does `kept` suppress `cand`?  The reference keeps a box iff `iou <= iou_threshold`
+// (ssd_output_decoder.py:91; NaN => dropped) with iou = RN(inter / union).  `quick` (both boxes
+// regular, 0 < thr finite) enables two exact shortcuts that avoid the division:
+//   - disjoint boxes: inter == 0, union > 0  =>  iou == +0 <= thr: kept;
+//   - with p = thr * union: inter <= p (1 - e) implies RN(inter/union) < thr and inter >= p (1 + e)
+//     implies RN(inter/union) > thr for e = 2^-48 (2^-20 in float32): each rounding contributes at
+//     most half an ulp (2^-53 / 2^-24 relative), far inside the guard band.  Only pairs inside the
+//     band take the exact division.
+template <typename T> struct GuardBand;
+template <> struct GuardBand<double> { static constexpr double lo = 1.0 - 0x1p-48, hi = 1.0 + 0x1p-48; };
+template <> struct GuardBand<float> { static constexpr float lo = 1.0f - 0x1p-20f, hi = 1.0f + 0x1p-20f; };
+
 template <typename IouT, bool TF>
-__device__ __forceinline__ bool suppresses(const Box<IouT>& kept, const Box<IouT>& cand, IouT thr) {
-    if (TF) {
-        return false;
-    } else {
-        // kept iff `similarities <= iou_threshold` (ssd_output_decoder.py:91); NaN => dropped
-        return !(iou_boxes<IouT>(cand, kept) <= thr);
+__device__ __forceinline__ bool suppresses(const Box<IouT>& kept, const Box<IouT>& cand, IouT thr, bool quick) {
+    if (quick) {
+        if (boxes_disjoint(kept, cand)) return false;
+        const IouT sx = (cand.x1 < kept.x1 ? cand.x1 : kept.x1) - (cand.x0 > kept.x0 ? cand.x0 : kept.x0);
+        const IouT sy = (cand.y1 < kept.y1 ? cand.y1 : kept.y1) - (cand.y0 > kept.y0 ? cand.y0 : kept.y0);
+        const IouT inter = sx * sy;                      // both sides > 0 here, same value as iou_boxes
+        const IouT uni = cand.area + kept.area - inter;
+        const IouT p = thr * uni;
+        if (inter <= p * GuardBand<IouT>::lo) return false;
+        if (inter >= p * GuardBand<IouT>::hi) return true;
     }
+    return !(iou_boxes<IouT>(cand, kept) <= thr);
 }
 template <>
-__device__ __forceinline__ bool suppresses<float, true>(const Box<float>& kept, const Box<float>& cand, float thr) {
+__device__ __forceinline__ bool suppresses<float, true>(const Box<float>& kept, const Box<float>& cand, float thr, bool) {
     return iou_tf(cand, kept) > thr;
 }
+
+// In-register bitonic sort of 32*R keys (key e lives in register e / 32 of lane e % 32).
+template <typename KeyT, int R>
+__device__ __forceinline__ void warp_sort_multi(KeyT (&k)[R], bool by_anchor) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll
+        for (int jj = size >> 1; jj > 0; jj >>= 1) {
+            if (jj >= 32) {
+                const int rj = jj >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const int r2 = r | rj;
+                        const bool canonical = (((r << 5) | lane) & size) == 0;
+                        KeyT a = k[r], b = k[r2];
+                        const bool swap = canonical ? key_before(b, a, by_anchor) : key_before(a, b, by_anchor);
+                        if (swap) { k[r] = b; k[r2] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    KeyT o = shfl_xor_key(k[r], jj);
+                    const bool first_half = (lane & jj) == 0;
+                    const bool canonical = (((r << 5) | lane) & size) == 0;
+                    const bool take_other = (first_half == canonical) ? key_before(o, k[r], by_anchor)
+                                                                      : key_before(k[r], o, by_anchor);
+                    if (take_other) k[r] = o;
+                }
+            }
+        }
+    }
+}
+
+constexpr int NMS_REG_KEYS = 4;                 // segments of up to 128 candidates are sorted in registers
+constexpr int NMS_REG_MAX = 32 * NMS_REG_KEYS;
 
 template <typename StoreT, typename IouT, typename KeyT, bool TF>
 __global__ void __launch_bounds__(NMS_WARPS * 32)
@@ -290,6 +441,7 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
     const int total = counters[CNT_LIST + 0];
     const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
     const unsigned lt = (1u << lane) - 1u;
+    const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
 
     for (;;) {
         int idx = 0;
@@ -302,29 +454,61 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
         const int cap = (g.Kseg > 0) ? min(g.Kseg, n) : n;
         KeyT* kp = keys + (size_t)seg * g.A;
         const SBox<StoreT>* bx = boxes + (size_t)b * g.A;
-        const bool tiny = n <= 32;
+        const bool in_regs = n <= NMS_REG_MAX;
+        const bool by_anchor = !g.do_nms && (g.K <= 0 || n <= g.K);
+
+        // small segments: sort in registers (no sort kernel, no write-back of the sorted keys)
+        KeyT rk[NMS_REG_KEYS];
+        if (in_regs) {
+            if (n <= 32) {
+                KeyT k0 = (lane < n) ? kp[lane] : KeyT::lowest();
+                rk[0] = warp_sort(k0, by_anchor);
+#pragma unroll
+                for (int r = 1; r < NMS_REG_KEYS; ++r) rk[r] = KeyT::lowest();
+            } else if (n <= 64) {
+                KeyT two[2];
+                two[0] = kp[lane];
+                two[1] = (32 + lane < n) ? kp[32 + lane] : KeyT::lowest();
+                warp_sort_multi<KeyT, 2>(two, by_anchor);
+                rk[0] = two[0]; rk[1] = two[1];
+#pragma unroll
+                for (int r = 2; r < NMS_REG_KEYS; ++r) rk[r] = KeyT::lowest();
+            } else {
+#pragma unroll
+                for (int r = 0; r < NMS_REG_KEYS; ++r) rk[r] = (r * 32 + lane < n) ? kp[r * 32 + lane] : KeyT::lowest();
+                warp_sort_multi<KeyT, NMS_REG_KEYS>(rk, by_anchor);
+            }
+        }
 
         if (!g.do_nms) {
             // `if iou_threshold:` falsy (ssd_output_decoder.py:326): every candidate is kept.
-            if (tiny) {
-                const bool by_anchor = (g.K <= 0 || n <= g.K);
-                KeyT k = (lane < n) ? kp[lane] : KeyT::lowest();
-                k = warp_sort(k, by_anchor);
-                if (lane < n) kp[lane] = k;
+            if (in_regs) {
+#pragma unroll
+                for (int r = 0; r < NMS_REG_KEYS; ++r)
+                    if (r * 32 + lane < n) kp[r * 32 + lane] = rk[r];
             }
             if (lane == 0) kept_count[seg] = cap;
             continue;
         }
 
         int nkept = 0;
+        bool quick = thr_ok && !TF;              // cleared as soon as an irregular box shows up
         for (int t0 = 0; t0 < n && nkept < cap; t0 += 32) {
             const int i = t0 + lane;
-            KeyT key = (i < n) ? kp[i] : KeyT::lowest();
-            if (tiny) key = warp_sort(key, false);       // small segments are sorted in registers
             const bool valid = i < n;
+            KeyT key;
+            if (in_regs) {
+                const int r = t0 >> 5;
+                key = rk[0];
+#pragma unroll
+                for (int q = 1; q < NMS_REG_KEYS; ++q) if (r == q) key = rk[q];
+            } else {
+                key = valid ? kp[i] : KeyT::lowest();
+            }
             Box<IouT> me;
             if (valid) me = load_box<StoreT, IouT>(bx, key.anchor(), sx, sy, d);
-            else { me.x0 = me.y0 = me.x1 = me.y1 = me.area = IouT(0); }
+            else { me.x0 = me.y0 = me.x1 = me.y1 = IouT(0); me.area = IouT(1); }
+            if (quick && __any_sync(0xffffffffu, valid && !box_regular(me))) quick = false;
             bool alive = valid;
 
             // against everything kept so far
@@ -333,7 +517,7 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
                 Box<IouT> kb;
                 if (k < KS) kb = cache[k];
                 else kb = load_box<StoreT, IouT>(bx, kp[k].anchor(), sx, sy, d);
-                if (alive && suppresses<IouT, TF>(kb, me, thr)) alive = false;
+                if (alive && suppresses<IouT, TF>(kb, me, thr, quick)) alive = false;
             }
 
             // among the 32 candidates of this step, in canonical order
@@ -350,7 +534,7 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
                     break;
                 }
                 Box<IouT> kb = tile[j];
-                if (lane > j && alive && suppresses<IouT, TF>(kb, me, thr)) alive = false;
+                if (lane > j && alive && suppresses<IouT, TF>(kb, me, thr, quick)) alive = false;
                 m = __ballot_sync(0xffffffffu, alive);
                 rem &= m;
             }
@@ -506,6 +690,144 @@ emit_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
     }
 }
 
+// ---- D4 (main path): one warp per image, k-way merge of the per-class keep lists --------------
+// Every class list is already in canonical order (score desc, anchor asc), so the cross-class
+// top-k (ssd_output_decoder.py:219-221) is a k-way merge that stops after `cnt` rows: lane l owns
+// the lists l, l+32, ..; each round a warp-wide max picks the next row.  Ties between classes go
+// to the lower class id, then the lower anchor (composite key).  The lists are staged in shared
+// memory when they fit.
+constexpr int MERGE_Q = 4;            // lists per lane => up to 128 segments per image
+
+template <typename KeyT> struct Comp;
+template <> struct Comp<Key64> {       // [score bits 32 | ~class 8 | ~anchor 24]
+    typedef uint64_t type;
+    __device__ __forceinline__ static type make(const Key64& k, int cls) {
+        return (k.v & 0xffffffff00000000ull) | ((uint64_t)(0xffu - (uint32_t)cls) << 24) | (uint64_t)(0xffffffu - k.anchor());
+    }
+    __device__ __forceinline__ static type lowest() { return 0; }
+    __device__ __forceinline__ static bool gt(type a, type b) { return a > b; }
+    __device__ __forceinline__ static bool eq(type a, type b) { return a == b; }
+    __device__ __forceinline__ static type shfl_xor(type a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+    __device__ __forceinline__ static int cls(type a) { return (int)(0xffu - (uint32_t)((a >> 24) & 0xffu)); }
+    __device__ __forceinline__ static uint32_t anchor(type a) { return 0xffffffu - (uint32_t)(a & 0xffffffu); }
+    __device__ __forceinline__ static double score(type a) { return (double)unord32((uint32_t)(a >> 32)); }
+};
+template <> struct Comp<Key128> {      // hi = score bits, lo = [~class 32 | ~anchor 32]
+    typedef Key128 type;
+    __device__ __forceinline__ static type make(const Key128& k, int cls) {
+        Key128 c; c.hi = k.hi; c.lo = ((uint64_t)(0xffffffffu - (uint32_t)cls) << 32) | (uint64_t)(0xffffffffu - k.anchor()); return c;
+    }
+    __device__ __forceinline__ static type lowest() { return Key128::lowest(); }
+    __device__ __forceinline__ static bool gt(const type& a, const type& b) { return (a.hi > b.hi) || (a.hi == b.hi && a.lo > b.lo); }
+    __device__ __forceinline__ static bool eq(const type& a, const type& b) { return a.hi == b.hi && a.lo == b.lo; }
+    __device__ __forceinline__ static type shfl_xor(const type& a, int m) { return shfl_xor_key(a, m); }
+    __device__ __forceinline__ static int cls(const type& a) { return (int)(0xffffffffu - (uint32_t)(a.lo >> 32)); }
+    __device__ __forceinline__ static uint32_t anchor(const type& a) { return 0xffffffffu - (uint32_t)a.lo; }
+    __device__ __forceinline__ static double score(const type& a) { return unord64(a.hi); }
+};
+
+template <typename StoreT, typename IouT, typename KeyT, bool SMEM>
+__global__ void __launch_bounds__(32)
+emit_merge_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
+                  const int* __restrict__ out_count, const long long* __restrict__ row_offset,
+                  const SBox<StoreT>* __restrict__ boxes, const int* __restrict__ aux_class, DecodeArgs g,
+                  int Kcap, double* __restrict__ rows, int* __restrict__ anchors) {
+    typedef Comp<KeyT> CK;
+    typedef typename CK::type ck_t;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeyT* sk = reinterpret_cast<KeyT*>(smem_raw);
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int NS = g.NS;
+    const int cnt = out_count[b];
+    if (cnt == 0) return;
+    const long long off = row_offset[b];
+    const SBox<StoreT>* bx = boxes + (size_t)b * g.A;
+    const int* cls_of = aux_class ? aux_class + (size_t)b * g.A : nullptr;
+    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy;
+    const KeyT* kbase = keys + (size_t)b * NS * g.A;
+
+    int len[MERGE_Q];
+    int T = 0;
+#pragma unroll
+    for (int q = 0; q < MERGE_Q; ++q) {
+        const int s = lane + 32 * q;
+        len[q] = (s < NS) ? kept_count[(size_t)b * NS + s] : 0;
+        T += len[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) T += __shfl_xor_sync(0xffffffffu, T, o);
+
+    if ((T <= cnt && !g.always_sort) || NS == 1) {
+        // no truncation: classes ascending, inside a class the NMS keep order (:212-218)
+        int base = 0;
+        for (int s = 0; s < NS; ++s) {
+            int k = 0;
+#pragma unroll
+            for (int q = 0; q < MERGE_Q; ++q) if ((s >> 5) == q) k = len[q];
+            k = __shfl_sync(0xffffffffu, k, s & 31);
+            if (k > cnt - base) k = cnt - base;            // (NS == 1 and always_sort: list longer than top_k)
+            const KeyT* kp = kbase + (size_t)s * g.A;
+            for (int r = lane; r < k; r += 32) {
+                const KeyT key = kp[r];
+                const uint32_t anchor = key.anchor();
+                const int cls = (NS > 1) ? (s + 1) : cls_of[anchor];
+                write_row<StoreT, IouT>(rows, anchors, off + base + r, cls, key.score(), anchor, bx, sx, sy);
+            }
+            base += k;
+        }
+        return;
+    }
+
+    if (SMEM) {
+        for (int s = 0; s < NS; ++s) {
+            int k = 0;
+#pragma unroll
+            for (int q = 0; q < MERGE_Q; ++q) if ((s >> 5) == q) k = len[q];
+            k = min(__shfl_sync(0xffffffffu, k, s & 31), Kcap);
+            const KeyT* kp = kbase + (size_t)s * g.A;
+            for (int r = lane; r < k; r += 32) sk[(size_t)s * Kcap + r] = kp[r];
+        }
+        __syncwarp();
+    }
+    auto fetch = [&](int s, int pos) -> KeyT {
+        return SMEM ? sk[(size_t)s * Kcap + pos] : kbase[(size_t)s * g.A + pos];
+    };
+    int cur[MERGE_Q];
+    ck_t head[MERGE_Q];
+#pragma unroll
+    for (int q = 0; q < MERGE_Q; ++q) {
+        cur[q] = 0;
+        head[q] = (len[q] > 0) ? CK::make(fetch(lane + 32 * q, 0), lane + 32 * q + 1) : CK::lowest();
+    }
+    ck_t outk = CK::lowest();
+    for (int r = 0; r < cnt; ++r) {
+        ck_t mine = head[0];
+#pragma unroll
+        for (int q = 1; q < MERGE_Q; ++q) if (CK::gt(head[q], mine)) mine = head[q];
+        ck_t best = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ck_t other = CK::shfl_xor(best, o);
+            if (CK::gt(other, best)) best = other;
+        }
+        if ((r & 31) == lane) outk = best;
+        if (CK::eq(mine, best)) {                       // keys are unique: exactly one lane advances
+#pragma unroll
+            for (int q = 0; q < MERGE_Q; ++q) {
+                if (CK::eq(head[q], best)) {
+                    ++cur[q];
+                    head[q] = (cur[q] < len[q]) ? CK::make(fetch(lane + 32 * q, cur[q]), lane + 32 * q + 1) : CK::lowest();
+                }
+            }
+        }
+        if ((r & 31) == 31 || r == cnt - 1) {
+            if (lane <= (r & 31))
+                write_row<StoreT, IouT>(rows, anchors, off + (r & ~31) + lane, CK::cls(outk), CK::score(outk),
+                                        CK::anchor(outk), bx, sx, sy);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
@@ -568,23 +890,44 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
     // D1
     {
         constexpr int V = 16 / (int)sizeof(InT);
-        size_t tile_bytes = (((size_t)g.tile_rows * g.W + V) * sizeof(InT) + 15) & ~(size_t)15;
-        size_t smem = tile_bytes + sizeof(int) * ((size_t)2 * g.NS + (size_t)(D1_THREADS / 32) * g.NS);
-        dim3 grid((unsigned)((size_t)B * g.tiles));
         LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
-        if (fast) {
-            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_filter_kernel<InT, true><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+        const size_t row_bytes = (size_t)g.W * sizeof(InT);
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (((size_t)g.A * row_bytes) % 16 == 0) &&
+                            (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
+        if (tma_ok) {
+            const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
+            const size_t smem = stage_bytes * D1_STAGES;
+            int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (ctas_per_sm > 4) ctas_per_sm = 4;
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            const long long total_tiles = (long long)B * g.tiles;
+            long long grid = (long long)d->sm_count * ctas_per_sm;
+            if (grid > total_tiles) grid = total_tiles;
+            if (fast) {
+                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+            } else {
+                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+            }
+            SSDC_TRY(check_launch("decode_filter_tma_kernel"));
         } else {
-            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_filter_kernel<InT, false><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+            size_t smem = (((size_t)g.tile_rows * g.W + V) * sizeof(InT) + 15) & ~(size_t)15;
+            dim3 grid((unsigned)((size_t)B * g.tiles));
+            if (fast) {
+                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                decode_filter_kernel<InT, true><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+            } else {
+                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                decode_filter_kernel<InT, false><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+            }
+            SSDC_TRY(check_launch("decode_filter_kernel"));
         }
-        SSDC_TRY(check_launch("decode_filter_kernel"));
     }
     // plan
     {
         LaunchScope ls(ctx, d, SSDC_K_PLAN);
-        plan_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(seg_count, (int)nseg, kept_count, lists, counters, n1, n2, n3);
+        plan_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(seg_count, (int)nseg, kept_count, lists, counters, NMS_REG_MAX, n1, n2, n3);
         SSDC_TRY(check_launch("plan_kernel"));
     }
     // D2: one persistent launch per size bin
@@ -594,7 +937,7 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
         const BinCfg cfg[4] = {{n1, 128, 8}, {n2, 512, 3}, {n3, 1024, 1}, {0, 1024, 1}};
         for (int k = 1; k <= 4; ++k) {
             const BinCfg& c = cfg[k - 1];
-            if (k < 4 && (size_t)g.A <= (size_t)(k == 1 ? 32 : cfg[k - 2].nmax)) continue;   // bin cannot occur
+            if (k < 4 && (size_t)g.A <= (size_t)(k == 1 ? NMS_REG_MAX : cfg[k - 2].nmax)) continue;   // bin cannot occur
             if (k == 4 && g.A <= n3) continue;
             LaunchScope ls(ctx, d, SSDC_K_SORT);
             if (k < 4) {
@@ -656,8 +999,28 @@ static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
         stride = (int)s;
         SSDC_TRY(d->merge_scratch.ensure((size_t)B * s * sizeof(Key128)));
     }
-    size_t smem = (size_t)EMIT_SMEM_KEYS * sizeof(Key128);
+    const int Kcap = (g.Kseg > 0) ? min(g.Kseg, g.A) : g.A;
     LaunchScope ls(ctx, d, SSDC_K_MERGE);
+    if (g.NS <= 32 * MERGE_Q && g.A < (1 << 24) && g.C <= 256) {
+        // warp-per-image k-way merge
+        const size_t list_bytes = may_sort ? (size_t)g.NS * Kcap * sizeof(KeyT) : 0;
+        const bool use_smem = g.NS > 1 && list_bytes > 0 && list_bytes <= 100 * 1024;
+        if (use_smem) {
+            SSDC_CUDA(cudaFuncSetAttribute(emit_merge_kernel<InT, IouT, KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)list_bytes));
+            emit_merge_kernel<InT, IouT, KeyT, true><<<(unsigned)B, 32, list_bytes, d->stream>>>(
+                d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
+                d->boxes.as<SBox<InT>>(), fast ? d->aux_class.as<int>() : nullptr, g, Kcap,
+                d->out_rows.as<double>(), d->out_anchor.as<int>());
+        } else {
+            emit_merge_kernel<InT, IouT, KeyT, false><<<(unsigned)B, 32, 0, d->stream>>>(
+                d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
+                d->boxes.as<SBox<InT>>(), fast ? d->aux_class.as<int>() : nullptr, g, Kcap,
+                d->out_rows.as<double>(), d->out_anchor.as<int>());
+        }
+        SSDC_TRY(check_launch("emit_merge_kernel"));
+        return SSDC_OK;
+    }
+    size_t smem = (size_t)EMIT_SMEM_KEYS * sizeof(Key128);
     SSDC_CUDA(cudaFuncSetAttribute(emit_kernel<InT, IouT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     emit_kernel<InT, IouT, KeyT><<<(unsigned)B, EMIT_THREADS, smem, d->stream>>>(
         d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
@@ -842,10 +1205,10 @@ int greedy_nms_dev(ssdc_ctx* ctx, DevCtx* d, const double* boxes, const double* 
     }
     {
         LaunchScope ls(ctx, d, SSDC_K_PLAN);
-        plan_kernel<<<1, 256, 0, st>>>(seg_count, 1, kept_count, lists, counters, n1, n2, n3);
+        plan_kernel<<<1, 256, 0, st>>>(seg_count, 1, kept_count, lists, counters, NMS_REG_MAX, n1, n2, n3);
         SSDC_TRY(check_launch("plan_kernel"));
     }
-    if (n > 32) {
+    if (n > NMS_REG_MAX) {
         LaunchScope ls(ctx, d, SSDC_K_SORT);
         int bin = n > n3 ? 4 : (n > n2 ? 3 : (n > n1 ? 2 : 1));
         if (bin < 4) {

@@ -144,14 +144,33 @@ __global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, 
 }
 
 // ---------------------------------------------------------------------------
+// Exact shortcuts for the ground-truth x anchor IoU (both boxes "regular": finite, area term > 0):
+//   disjoint boxes                      => iou == +0 exactly;
+//   iou <= min(a1, a2) / max(a1, a2)    (inter <= smaller area, union >= larger area), so a pair
+//   whose area ratio is below a bound (with a 2^-40 guard for the roundings) is below that bound.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool regular_d(const Box<double>& b) { return b.area > 0.0 && b.area < INFINITY; }
+__device__ __forceinline__ bool disjoint_d(const Box<double>& a, const Box<double>& b) {
+    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
+}
+__device__ __forceinline__ bool ratio_below(const Box<double>& a, const Box<double>& b, double bound_lo) {
+    const double mn = a.area < b.area ? a.area : b.area;
+    const double mx = a.area < b.area ? b.area : a.area;
+    return mn < bound_lo * mx;
+}
+constexpr double GUARD_LO = 1.0 - 0x1p-40;
+
+// ---------------------------------------------------------------------------
 // E1: per GT row, best anchor inside one chunk of anchors
 // ---------------------------------------------------------------------------
+constexpr int E1_GROUP = 64;      // GT rows reduced per block-level pass
+
 __global__ void __launch_bounds__(E1_THREADS)
 rowbest_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
                const Box<double>* __restrict__ abox, EncArgs g,
                double* __restrict__ part_val, int* __restrict__ part_idx, int* __restrict__ irregular) {
-    __shared__ double s_val[E1_THREADS / 32];
-    __shared__ int s_idx[E1_THREADS / 32];
+    __shared__ double s_val[E1_THREADS / 32][E1_GROUP];
+    __shared__ int s_idx[E1_THREADS / 32][E1_GROUP];
     const int chunk = blockIdx.x % g.chunks;
     const int b = blockIdx.x / g.chunks;
     const long long g0 = gt_off[b], g1 = gt_off[b + 1];
@@ -162,38 +181,53 @@ rowbest_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_
 
     Box<double> ab[E1_PER_THREAD];
     int ai[E1_PER_THREAD];
+    bool areg[E1_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < E1_PER_THREAD; ++k) {
         ai[k] = a_base + k * E1_THREADS + tid;
-        if (ai[k] < g.A) ab[k] = abox[ai[k]];
+        areg[k] = false;
+        if (ai[k] < g.A) { ab[k] = abox[ai[k]]; areg[k] = regular_d(ab[k]); }
     }
     bool irr = false;
-    for (int r = 0; r < m; ++r) {
-        const Box<double> gb = gtp[g0 + r].box;
-        double bv = -INFINITY;
-        int bi = 0x7fffffff;
+    for (int r0 = 0; r0 < m; r0 += E1_GROUP) {
+        const int rn = min(E1_GROUP, m - r0);
+        for (int rr = 0; rr < rn; ++rr) {
+            const Box<double> gb = gtp[g0 + r0 + rr].box;
+            const bool greg = regular_d(gb);
+            double bv = -INFINITY;
+            int bi = 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < E1_PER_THREAD; ++k) {
-            if (ai[k] < g.A) {
-                double s = iou_boxes<double>(gb, ab[k]);
-                irr |= (s < 0.0);
-                if (better(s, ai[k], bv, bi)) { bv = s; bi = ai[k]; }
+            for (int k = 0; k < E1_PER_THREAD; ++k) {
+                if (ai[k] < g.A) {
+                    double s;
+                    if (greg && areg[k]) {
+                        if (disjoint_d(gb, ab[k])) s = 0.0;
+                        else if (bv > 0.0 && ratio_below(gb, ab[k], bv * GUARD_LO)) continue;   // cannot reach the running best
+                        else s = iou_boxes<double>(gb, ab[k]);
+                    } else {
+                        s = iou_boxes<double>(gb, ab[k]);
+                        irr |= (s < 0.0);
+                    }
+                    if (better(s, ai[k], bv, bi)) { bv = s; bi = ai[k]; }
+                }
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { s_val[warp][rr] = bv; s_idx[warp][rr] = bi; }
         }
-        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < rn) {
+            double bv = s_val[0][tid];
+            int bi = s_idx[0][tid];
 #pragma unroll
             for (int w = 1; w < E1_THREADS / 32; ++w)
-                if (better(s_val[w], s_idx[w], bv, bi)) { bv = s_val[w]; bi = s_idx[w]; }
-            part_val[(size_t)(g0 + r) * g.chunks + chunk] = bv;
-            part_idx[(size_t)(g0 + r) * g.chunks + chunk] = bi;
+                if (better(s_val[w][tid], s_idx[w][tid], bv, bi)) { bv = s_val[w][tid]; bi = s_idx[w][tid]; }
+            part_val[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = bv;
+            part_idx[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = bi;
         }
         __syncthreads();
     }
@@ -201,87 +235,128 @@ rowbest_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_
 }
 
 // ---------------------------------------------------------------------------
-// E2: greedy bipartite rounds, one warp per image
+// E2: greedy bipartite rounds (matching_utils.py:63-77), one CTA per image
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, int B,
+constexpr int E2_THREADS = 256;
+
+// best column of ground-truth row `r` inside chunk `c`, with the taken columns zeroed
+__device__ __forceinline__ void rescan_chunk(const Box<double>& gb, const Box<double>* __restrict__ abox, int A, int c,
+                                             const unsigned* taken_bits, double* red_val, int* red_idx,
+                                             double* out_val, int* out_idx) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool greg = regular_d(gb);
+    double bv = -INFINITY; int bi = 0x7fffffff;
+    for (int a = c * E1_CHUNK + tid; a < min(A, (c + 1) * E1_CHUNK); a += E2_THREADS) {
+        double s;
+        if ((taken_bits[a >> 5] >> (a & 31)) & 1u) s = 0.0;
+        else {
+            const Box<double> ab = abox[a];
+            if (greg && regular_d(ab) && disjoint_d(gb, ab)) s = 0.0;
+            else s = iou_boxes<double>(gb, ab);
+        }
+        if (better(s, a, bv, bi)) { bv = s; bi = a; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_val[warp] = bv; red_idx[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < E2_THREADS / 32; ++w)
+            if (better(red_val[w], red_idx[w], bv, bi)) { bv = red_val[w]; bi = red_idx[w]; }
+        *out_val = bv; *out_idx = bi;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(E2_THREADS)
+match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
              const Box<double>* __restrict__ abox, EncArgs g,
-             const double* __restrict__ part_val, const int* __restrict__ part_idx,
-             const int* __restrict__ irregular,
-             double* __restrict__ rb_val, int* __restrict__ rb_idx, int* __restrict__ taken,
-             unsigned char* __restrict__ row_done, int* __restrict__ match) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= B) return;
+             double* __restrict__ part_val, int* __restrict__ part_idx,
+             const int* __restrict__ irregular, int* __restrict__ match) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_val[E2_THREADS / 32];
+    __shared__ int red_idx[E2_THREADS / 32];
+    __shared__ int s_asel;
+    const int b = blockIdx.x;
     const long long g0 = gt_off[b];
     const int m = (int)(gt_off[b + 1] - g0);
     if (m == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool irr = irregular[b] != 0;
+    const int nbits = (g.A + 31) >> 5;
+    // smem: row best value / index / done flag, bitmap of taken (zeroed) columns
+    double* rb_val = reinterpret_cast<double*>(smem_raw);
+    int* rb_idx = reinterpret_cast<int*>(rb_val + m);
+    unsigned* taken_bits = reinterpret_cast<unsigned*>(rb_idx + m);
+    unsigned char* done = reinterpret_cast<unsigned char*>(taken_bits + nbits);
 
-    // initial row argmax: reduce the chunk partials
-    for (int r = 0; r < m; ++r) {
+    for (int i = tid; i < nbits; i += E2_THREADS) taken_bits[i] = 0;
+    for (int r = tid; r < m; r += E2_THREADS) {
         double bv = -INFINITY; int bi = 0x7fffffff;
-        for (int c = lane; c < g.chunks; c += 32) {
-            double v = part_val[(size_t)(g0 + r) * g.chunks + c];
-            int i = part_idx[(size_t)(g0 + r) * g.chunks + c];
+        for (int c = 0; c < g.chunks; ++c) {
+            const double v = part_val[(size_t)(g0 + r) * g.chunks + c];
+            const int i = part_idx[(size_t)(g0 + r) * g.chunks + c];
             if (better(v, i, bv, bi)) { bv = v; bi = i; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { rb_val[g0 + r] = bv; rb_idx[g0 + r] = bi; row_done[g0 + r] = 0; match[g0 + r] = 0; }
+        rb_val[r] = bv; rb_idx[r] = bi; done[r] = 0;
+        match[g0 + r] = 0;
     }
-    __syncwarp();
+    __syncthreads();
 
-    // matching_utils.py:63-77: exactly m rounds
     for (int round = 0; round < m; ++round) {
-        // ground_truth_index = np.argmax(overlaps)
-        double bv = -INFINITY; int bg = 0x7fffffff;
-        for (int r = lane; r < m; r += 32) {
-            double v = rb_val[g0 + r];
-            if (better(v, r, bv, bg)) { bv = v; bg = r; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int og = __shfl_xor_sync(0xffffffffu, bg, o);
-            if (better(ov, og, bv, bg)) { bv = ov; bg = og; }
-        }
-        const int gsel = bg;
-        const int asel = rb_idx[g0 + gsel];
-        __syncwarp();
-        if (lane == 0) {
-            match[g0 + gsel] = asel;
-            rb_val[g0 + gsel] = 0.0;      // weight_matrix[ground_truth_index] = 0  -> argmax 0, weight 0
-            rb_idx[g0 + gsel] = 0;
-            row_done[g0 + gsel] = 1;
-            taken[g0 + round] = asel;     // weight_matrix[:, anchor_index] = 0
-        }
-        __syncwarp();
-        // rows whose best column was just zeroed must be rescanned
-        for (int r = 0; r < m; ++r) {
-            if (row_done[g0 + r]) continue;
-            if (!irr && rb_idx[g0 + r] != asel) continue;
-            const Box<double> gb = gtp[g0 + r].box;
-            double rv = -INFINITY; int ri = 0x7fffffff;
-            for (int a = lane; a < g.A; a += 32) {
-                double s = iou_boxes<double>(gb, abox[a]);
-                for (int t = 0; t <= round; ++t)
-                    if (taken[g0 + t] == a) s = 0.0;
-                if (better(s, a, rv, ri)) { rv = s; ri = a; }
+        if (warp == 0) {
+            // ground_truth_index = np.argmax(overlaps): matched (zeroed) rows take part with weight 0
+            double bv = -INFINITY; int bg = 0x7fffffff;
+            for (int r = lane; r < m; r += 32) {
+                const double v = rb_val[r];
+                if (better(v, r, bv, bg)) { bv = v; bg = r; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, rv, o);
-                int oi = __shfl_xor_sync(0xffffffffu, ri, o);
-                if (better(ov, oi, rv, ri)) { rv = ov; ri = oi; }
+                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int og = __shfl_xor_sync(0xffffffffu, bg, o);
+                if (better(ov, og, bv, bg)) { bv = ov; bg = og; }
             }
-            if (lane == 0) { rb_val[g0 + r] = rv; rb_idx[g0 + r] = ri; }
+            if (lane == 0) {
+                const int asel = rb_idx[bg];
+                match[g0 + bg] = asel;
+                rb_val[bg] = 0.0;          // weight_matrix[ground_truth_index] = 0 -> argmax 0, weight 0
+                rb_idx[bg] = 0;
+                done[bg] = 1;
+                taken_bits[asel >> 5] |= 1u << (asel & 31);     // weight_matrix[:, anchor_index] = 0
+                s_asel = asel;
+            }
         }
-        __syncwarp();
+        __syncthreads();
+        const int asel = s_asel;
+        // rows whose best column was just zeroed get a new best: only the chunks whose stored best
+        // is a zeroed column have to be rescanned (everything, every round, for irregular inputs)
+        for (int r = 0; r < m; ++r) {
+            if (done[r]) continue;
+            if (!irr && rb_idx[r] != asel) continue;
+            const Box<double> gb = gtp[g0 + r].box;
+            for (int c = 0; c < g.chunks; ++c) {
+                const int pi = part_idx[(size_t)(g0 + r) * g.chunks + c];
+                if (irr || ((taken_bits[pi >> 5] >> (pi & 31)) & 1u))
+                    rescan_chunk(gb, abox, g.A, c, taken_bits, red_val, red_idx,
+                                 &part_val[(size_t)(g0 + r) * g.chunks + c], &part_idx[(size_t)(g0 + r) * g.chunks + c]);
+            }
+            if (tid == 0) {
+                double bv = -INFINITY; int bi = 0x7fffffff;
+                for (int c = 0; c < g.chunks; ++c) {
+                    const double v = part_val[(size_t)(g0 + r) * g.chunks + c];
+                    const int i = part_idx[(size_t)(g0 + r) * g.chunks + c];
+                    if (better(v, i, bv, bi)) { bv = v; bi = i; }
+                }
+                rb_val[r] = bv; rb_idx[r] = bi;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
     }
 }
 
@@ -301,7 +376,7 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
              double* __restrict__ y, double* __restrict__ y2, int* __restrict__ midx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RowMeta* meta = reinterpret_cast<RowMeta*>(smem_raw);               // E3_ROWS
-    Box<double>* sgt = reinterpret_cast<Box<double>*>(meta + E3_ROWS);   // up to smem_gt boxes
+    Box<double>* sgt = reinterpret_cast<Box<double>*>(meta + E3_ROWS);   // the image's GT boxes
     const int tile = blockIdx.x % tiles;
     const int b = blockIdx.x / tiles;
     const int a0 = tile * E3_ROWS;
@@ -310,10 +385,15 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
     const int m = (int)(gt_off[b + 1] - g0);
     const int tid = threadIdx.x;
 
-    // stage the image's GT boxes and bipartite matches (dynamic smem sized for the batch's max m)
     int* smatch = reinterpret_cast<int*>(sgt + m);
     for (int r = tid; r < m; r += E3_THREADS) { sgt[r] = gtp[g0 + r].box; smatch[r] = match[g0 + r]; }
     __syncthreads();
+
+    // pairs whose IoU is certainly below both thresholds never influence a decision (they can be
+    // neither a match nor make the anchor neutral, nor be the argmax among pairs that do)
+    const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
+    const bool prune = thr_min > 0.0 && thr_min < INFINITY;
+    const double prune_lo = thr_min * GUARD_LO;
 
     if (tid < rows) {
         const int a = a0 + tid;
@@ -321,6 +401,7 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
         bool neutral = false;
         if (m > 0) {
             const Box<double> ab = abox[a];
+            const bool areg = regular_d(ab);
             // bipartite assignment: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (last write wins)
             int bip = -1;
             for (int r = 0; r < m; ++r) if (smatch[r] == a) bip = r;
@@ -329,7 +410,15 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
             if (bip >= 0) { cv = 0.0; cg = 0; }
             else {
                 for (int r = 0; r < m; ++r) {
-                    double s = iou_boxes<double>(sgt[r], ab);
+                    const Box<double> gb = sgt[r];
+                    double s;
+                    if (areg && regular_d(gb)) {
+                        if (disjoint_d(gb, ab)) s = 0.0;
+                        else if (prune && ratio_below(gb, ab, prune_lo)) s = 0.0;   // stands for "below thr_min"
+                        else s = iou_boxes<double>(gb, ab);
+                    } else {
+                        s = iou_boxes<double>(gb, ab);
+                    }
                     if (better(s, r, cv, cg)) { cv = s; cg = r; }
                 }
             }
@@ -361,23 +450,53 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
     }
     __syncthreads();
 
-    // stream the tile out: element e of the tile is (row e / W, column e % W)
+    // stream the tile out: element e of the tile is (row e / W, column e % W); 16-byte stores when
+    // the tile starts on a 16-byte boundary
     const int W = g.W, C = g.C;
     const int n = rows * W;
-    double* out = y + ((size_t)b * g.A + a0) * W;
-    double* out2 = y2 ? y2 + ((size_t)b * g.A + a0) * W : nullptr;
+    const size_t base = ((size_t)b * g.A + a0) * W;
+    double* out = y + base;
+    double* out2 = y2 ? y2 + base : nullptr;
     const double* tl = tail + (size_t)a0 * 12;
-    int r = tid / W, c = tid % W;
-    const int dr = E3_THREADS / W, dc = E3_THREADS % W;
-    for (int e = tid; e < n; e += E3_THREADS) {
-        double v;
-        if (c < C) v = (c == meta[r].cls) ? 1.0 : 0.0;
-        else if (c < C + 4) v = meta[r].off[c - C];
-        else v = tl[(size_t)r * 12 + (c - C)];
-        out[e] = v;
-        if (out2) out2[e] = (c >= C && c < C + 4) ? 0.0 : v;
-        r += dr; c += dc;
-        if (c >= W) { c -= W; ++r; }
+    const float inv_w = 1.0f / (float)W;
+    auto value = [&](int e) -> double {
+        const int r = (int)(((float)e + 0.5f) * inv_w);
+        const int c = e - r * W;
+        if (c < C) return (c == meta[r].cls) ? 1.0 : 0.0;
+        if (c < C + 4) return meta[r].off[c - C];
+        return tl[(size_t)r * 12 + (c - C)];
+    };
+    auto value2 = [&](int e, double v) -> double {
+        const int r = (int)(((float)e + 0.5f) * inv_w);
+        const int c = e - r * W;
+        return (c >= C && c < C + 4) ? 0.0 : v;
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (!out2 || (reinterpret_cast<uintptr_t>(out2) & 15) == 0);
+    if (vec) {
+        const int npair = n >> 1;
+        for (int i = tid; i < npair; i += E3_THREADS) {
+            double2 v;
+            v.x = value(2 * i);
+            v.y = value(2 * i + 1);
+            reinterpret_cast<double2*>(out)[i] = v;
+            if (out2) {
+                double2 w;
+                w.x = value2(2 * i, v.x);
+                w.y = value2(2 * i + 1, v.y);
+                reinterpret_cast<double2*>(out2)[i] = w;
+            }
+        }
+        if ((n & 1) && tid == 0) {
+            const double v = value(n - 1);
+            out[n - 1] = v;
+            if (out2) out2[n - 1] = value2(n - 1, v);
+        }
+    } else {
+        for (int e = tid; e < n; e += E3_THREADS) {
+            const double v = value(e);
+            out[e] = v;
+            if (out2) out2[e] = value2(e, v);
+        }
     }
 }
 
@@ -428,20 +547,12 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
         size_t o_pv = carve((size_t)n_gt * g.chunks * sizeof(double));
         size_t o_pi = carve((size_t)n_gt * g.chunks * sizeof(int));
-        size_t o_rv = carve((size_t)n_gt * sizeof(double));
-        size_t o_ri = carve((size_t)n_gt * sizeof(int));
-        size_t o_tk = carve((size_t)n_gt * sizeof(int));
-        size_t o_dn = carve((size_t)n_gt);
         size_t o_mt = carve((size_t)n_gt * sizeof(int));
         size_t o_ir = carve((size_t)B * sizeof(int));
         SSDC_TRY(d->partial.ensure(off));
         char* base = d->partial.as<char>();
         double* part_val = reinterpret_cast<double*>(base + o_pv);
         int* part_idx = reinterpret_cast<int*>(base + o_pi);
-        double* rb_val = reinterpret_cast<double*>(base + o_rv);
-        int* rb_idx = reinterpret_cast<int*>(base + o_ri);
-        int* taken = reinterpret_cast<int*>(base + o_tk);
-        unsigned char* done = reinterpret_cast<unsigned char*>(base + o_dn);
         match = reinterpret_cast<int*>(base + o_mt);
         int* irregular = reinterpret_cast<int*>(base + o_ir);
         SSDC_CUDA(cudaMemsetAsync(irregular, 0, (size_t)B * sizeof(int), st));
@@ -457,8 +568,9 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         }
         {
             LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
-            match_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(gtp, gt_off, (int)B, abox, g, part_val, part_idx, irregular,
-                                                                   rb_val, rb_idx, taken, done, match);
+            const size_t smem = (size_t)max_m * (sizeof(double) + sizeof(int) + 1) + (size_t)((enc->A + 31) / 32) * sizeof(unsigned) + 64;
+            SSDC_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            match_kernel<<<(unsigned)B, E2_THREADS, smem, st>>>(gtp, gt_off, abox, g, part_val, part_idx, irregular, match);
             SSDC_TRY(check_launch("match_kernel"));
         }
     }
