@@ -349,46 +349,56 @@ __device__ __forceinline__ Box<IouT> load_box(const SBox<StoreT>* __restrict__ b
     return make_box<IouT>((IouT)s.x0 * sx, (IouT)s.y0 * sy, (IouT)s.x1 * sx, (IouT)s.y1 * sy, d);
 }
 
-// `regular`: finite coordinates and a finite positive area term.  For two regular boxes that do not
-// overlap, the reference's IoU is exactly +0 (inter = 0, union = a1 + a2 > 0), so the decision is
-// `0 <= thr` without evaluating the division.  The four comparisons imply
-// min(x1) <= max(x0) or min(y1) <= max(y0) for any boxes, i.e. a zero side length.
-template <typename T>
-__device__ __forceinline__ bool box_regular(const Box<T>& b) { return b.area > T(0) && b.area < T(INFINITY); }
-template <typename T>
-__device__ __forceinline__ bool boxes_disjoint(const Box<T>& a, const Box<T>& b) {
-    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
-}
-
-// Does `kept` suppress `cand`?  The reference keeps a box iff `iou <= iou_threshold`
-// (ssd_output_decoder.py:91; NaN => dropped) with iou = RN(inter / union).  `quick` (both boxes
-// regular, 0 < thr finite) enables two exact shortcuts that avoid the division:
-//   - disjoint boxes: inter == 0, union > 0  =>  iou == +0 <= thr: kept;
+// ---------------------------------------------------------------------------
+// Pair decisions.  The reference keeps a box iff `iou <= iou_threshold`
+// (ssd_output_decoder.py:91; NaN => dropped) with iou = RN(inter / union).
+//
+// `regular` box: x1 > x0, y1 > y0 and a finite positive area term.  For two regular boxes:
+//   - disjoint (a zero side length): inter == 0, union = a1 + a2 > 0  =>  iou == +0 exactly, so the
+//     pair is decided by `0 <= thr` alone.  Disjointness is tested on the RAW stored corners: the
+//     scaling by a positive image size is monotone, so raw-disjoint implies scaled-disjoint;
 //   - with p = thr * union: inter <= p (1 - e) implies RN(inter/union) < thr and inter >= p (1 + e)
-//     implies RN(inter/union) > thr for e = 2^-48 (2^-20 in float32): each rounding contributes at
+//     implies RN(inter/union) > thr for e = 2^-48 (2^-20 in float32): every rounding contributes at
 //     most half an ulp (2^-53 / 2^-24 relative), far inside the guard band.  Only pairs inside the
 //     band take the exact division.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ bool box_regular(const Box<T>& b) {
+    return b.x1 > b.x0 && b.y1 > b.y0 && b.area > T(0) && b.area < T(INFINITY);
+}
+template <typename T>
+__device__ __forceinline__ bool raw_disjoint(const SBox<T>& a, const SBox<T>& b) {
+    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
+}
 template <typename T> struct GuardBand;
 template <> struct GuardBand<double> { static constexpr double lo = 1.0 - 0x1p-48, hi = 1.0 + 0x1p-48; };
 template <> struct GuardBand<float> { static constexpr float lo = 1.0f - 0x1p-20f, hi = 1.0f + 0x1p-20f; };
 
+template <typename StoreT, typename IouT>
+__device__ __forceinline__ Box<IouT> scale_box(const SBox<StoreT>& s, IouT sx, IouT sy, IouT d) {
+    return make_box<IouT>((IouT)s.x0 * sx, (IouT)s.y0 * sy, (IouT)s.x1 * sx, (IouT)s.y1 * sy, d);
+}
+
+// Does `kept` suppress `cand`?
 template <typename IouT, bool TF>
-__device__ __forceinline__ bool suppresses(const Box<IouT>& kept, const Box<IouT>& cand, IouT thr, bool quick) {
-    if (quick) {
-        if (boxes_disjoint(kept, cand)) return false;
+__device__ __forceinline__ bool suppresses(const Box<IouT>& kept, const Box<IouT>& cand, IouT thr, bool thr_ok) {
+    if (TF) {
+        Box<float> a, b;
+        a.x0 = (float)cand.x0; a.y0 = (float)cand.y0; a.x1 = (float)cand.x1; a.y1 = (float)cand.y1; a.area = 0.f;
+        b.x0 = (float)kept.x0; b.y0 = (float)kept.y0; b.x1 = (float)kept.x1; b.y1 = (float)kept.y1; b.area = 0.f;
+        return iou_tf(a, b) > (float)thr;
+    }
+    if (thr_ok && box_regular(kept) && box_regular(cand)) {
         const IouT sx = (cand.x1 < kept.x1 ? cand.x1 : kept.x1) - (cand.x0 > kept.x0 ? cand.x0 : kept.x0);
         const IouT sy = (cand.y1 < kept.y1 ? cand.y1 : kept.y1) - (cand.y0 > kept.y0 ? cand.y0 : kept.y0);
-        const IouT inter = sx * sy;                      // both sides > 0 here, same value as iou_boxes
+        if (!(sx > IouT(0)) || !(sy > IouT(0))) return false;       // iou == +0 <= thr
+        const IouT inter = sx * sy;                                  // same value as iou_boxes computes
         const IouT uni = cand.area + kept.area - inter;
         const IouT p = thr * uni;
         if (inter <= p * GuardBand<IouT>::lo) return false;
         if (inter >= p * GuardBand<IouT>::hi) return true;
     }
     return !(iou_boxes<IouT>(cand, kept) <= thr);
-}
-template <>
-__device__ __forceinline__ bool suppresses<float, true>(const Box<float>& kept, const Box<float>& cand, float thr, bool) {
-    return iou_tf(cand, kept) > thr;
 }
 
 // In-register bitonic sort of 32*R keys (key e lives in register e / 32 of lane e % 32).
@@ -426,9 +436,47 @@ __device__ __forceinline__ void warp_sort_multi(KeyT (&k)[R], bool by_anchor) {
     }
 }
 
-constexpr int NMS_REG_KEYS = 4;                 // segments of up to 128 candidates are sorted in registers
-constexpr int NMS_REG_MAX = 32 * NMS_REG_KEYS;
+constexpr int NMS_SMEM_SORT = 128;              // segments of up to 128 candidates are sorted by the NMS warp itself
+constexpr int NMS_REG_MAX = NMS_SMEM_SORT;
+constexpr int NMS_QUEUE = 1024;                 // 16-bit pair entries: a full 32 x 32 block of pairs
 
+// Warp-level bitonic sort of N (power of two, <= NMS_SMEM_SORT) keys in shared memory.
+template <typename KeyT>
+__device__ __forceinline__ void warp_smem_sort(KeyT* s, int N, bool by_anchor) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+            for (int i = lane; i < (N >> 1); i += 32) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const KeyT a = s[lo], b = s[hi];
+                const bool canonical = (lo & k) == 0;
+                const bool swap = canonical ? key_before(b, a, by_anchor) : key_before(a, b, by_anchor);
+                if (swap) { s[lo] = b; s[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// The pair decision is called from two places; keeping one copy keeps the kernel inside the
+// instruction cache.
+template <typename StoreT, typename IouT, bool TF>
+__device__ __noinline__ bool decide_pair(SBox<StoreT> kept, SBox<StoreT> cand, IouT sx, IouT sy, IouT d, IouT thr, bool thr_ok) {
+    return suppresses<IouT, TF>(scale_box<StoreT, IouT>(kept, sx, sy, d), scale_box<StoreT, IouT>(cand, sx, sy, d), thr, thr_ok);
+}
+
+// D3.  One warp per segment.  Each step takes the next 32 candidates in canonical order:
+//   (1) kept phase: lane k screens kept box k against the step's 32 candidates with a cheap
+//       disjointness test on the raw corners (tight loop, no warp-wide synchronisation); only the
+//       overlapping pairs are queued in shared memory and decided 32 at a time with all lanes busy
+//       (these pairs are independent of one another);
+//   (2) the same screening + batched decisions for the pairs inside the step give each candidate the
+//       bit mask of the earlier candidates that would suppress it;
+//   (3) the greedy order is then resolved with scalar bit operations, stopping at the segment cap.
 template <typename StoreT, typename IouT, typename KeyT, bool TF>
 __global__ void __launch_bounds__(NMS_WARPS * 32)
 nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __restrict__ kept_count,
@@ -436,12 +484,40 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
            const SBox<StoreT>* __restrict__ boxes, DecodeArgs g, int KS) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Box<IouT>* cache = reinterpret_cast<Box<IouT>*>(smem_raw) + (size_t)warp * (KS + 32);
-    Box<IouT>* tile = cache + KS;
+    // per-warp shared memory: raw corners of the kept boxes (cache) and of the step's candidates,
+    // the sort buffer, the pair queue and the per-candidate suppression masks
+    const size_t per_warp = (size_t)(KS + 32) * sizeof(SBox<StoreT>) + (size_t)NMS_SMEM_SORT * sizeof(KeyT) +
+                            (size_t)NMS_QUEUE * sizeof(unsigned short) + 32 * sizeof(unsigned);
+    unsigned char* base = smem_raw + (size_t)warp * per_warp;
+    SBox<StoreT>* kraw = reinterpret_cast<SBox<StoreT>*>(base);
+    SBox<StoreT>* craw = kraw + KS;
+    KeyT* sbuf = reinterpret_cast<KeyT*>(craw + 32);
+    unsigned* sup = reinterpret_cast<unsigned*>(sbuf + NMS_SMEM_SORT);
+    unsigned short* queue = reinterpret_cast<unsigned short*>(sup + 32);
+
     const int total = counters[CNT_LIST + 0];
     const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
     const unsigned lt = (1u << lane) - 1u;
     const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
+    // the raw-corner screening is only exact for regular boxes, a usable threshold and positive scales
+    const bool screen_ok = thr_ok && g.sx > 0.0 && g.sy > 0.0;
+
+    // writes lane's set bits of `mask` as pairs (a << 5 | bit) behind one another; returns the total
+    auto enqueue = [&](unsigned mask, unsigned a) -> int {
+        const int np = __popc(mask);
+        int start = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, start, o);
+            if (lane >= o) start += v;
+        }
+        const int npairs = __shfl_sync(0xffffffffu, start, 31);
+        start -= np;
+        for (unsigned rem = mask; rem; rem &= rem - 1)
+            queue[start++] = (unsigned short)((a << 5) | (unsigned)(__ffs(rem) - 1));
+        __syncwarp();
+        return npairs;
+    };
 
     for (;;) {
         int idx = 0;
@@ -454,96 +530,139 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
         const int cap = (g.Kseg > 0) ? min(g.Kseg, n) : n;
         KeyT* kp = keys + (size_t)seg * g.A;
         const SBox<StoreT>* bx = boxes + (size_t)b * g.A;
-        const bool in_regs = n <= NMS_REG_MAX;
+        const bool local_sort = n <= NMS_SMEM_SORT;
         const bool by_anchor = !g.do_nms && (g.K <= 0 || n <= g.K);
 
-        // small segments: sort in registers (no sort kernel, no write-back of the sorted keys)
-        KeyT rk[NMS_REG_KEYS];
-        if (in_regs) {
-            if (n <= 32) {
-                KeyT k0 = (lane < n) ? kp[lane] : KeyT::lowest();
-                rk[0] = warp_sort(k0, by_anchor);
-#pragma unroll
-                for (int r = 1; r < NMS_REG_KEYS; ++r) rk[r] = KeyT::lowest();
-            } else if (n <= 64) {
-                KeyT two[2];
-                two[0] = kp[lane];
-                two[1] = (32 + lane < n) ? kp[32 + lane] : KeyT::lowest();
-                warp_sort_multi<KeyT, 2>(two, by_anchor);
-                rk[0] = two[0]; rk[1] = two[1];
-#pragma unroll
-                for (int r = 2; r < NMS_REG_KEYS; ++r) rk[r] = KeyT::lowest();
-            } else {
-#pragma unroll
-                for (int r = 0; r < NMS_REG_KEYS; ++r) rk[r] = (r * 32 + lane < n) ? kp[r * 32 + lane] : KeyT::lowest();
-                warp_sort_multi<KeyT, NMS_REG_KEYS>(rk, by_anchor);
-            }
-        }
-
         if (!g.do_nms) {
-            // `if iou_threshold:` falsy (ssd_output_decoder.py:326): every candidate is kept.
-            if (in_regs) {
-#pragma unroll
-                for (int r = 0; r < NMS_REG_KEYS; ++r)
-                    if (r * 32 + lane < n) kp[r * 32 + lane] = rk[r];
+            // `if iou_threshold:` falsy (ssd_output_decoder.py:326): every candidate is kept; small
+            // segments still have to be put in order here (larger ones were sorted by sort_kernel)
+            if (local_sort) {
+                const int N = pow2_ceil(n);
+                for (int i = lane; i < N; i += 32) sbuf[i] = (i < n) ? kp[i] : KeyT::lowest();
+                __syncwarp();
+                warp_smem_sort(sbuf, N, by_anchor);
+                for (int i = lane; i < n; i += 32) kp[i] = sbuf[i];
             }
             if (lane == 0) kept_count[seg] = cap;
             continue;
         }
 
+        // small segments are sorted here (no sort kernel, no write-back of the sorted keys):
+        // <= 64 keys in registers (shuffle network), <= 128 in shared memory
+        KeyT key0 = KeyT::lowest(), key1 = KeyT::lowest();
+        if (n <= 32) {
+            key0 = warp_sort((lane < n) ? kp[lane] : KeyT::lowest(), false);
+        } else if (n <= 64) {
+            KeyT two[2];
+            two[0] = kp[lane];
+            two[1] = (32 + lane < n) ? kp[32 + lane] : KeyT::lowest();
+            warp_sort_multi<KeyT, 2>(two, false);
+            key0 = two[0]; key1 = two[1];
+        } else if (local_sort) {
+            const int N = pow2_ceil(n);
+            for (int i = lane; i < N; i += 32) sbuf[i] = (i < n) ? kp[i] : KeyT::lowest();
+            __syncwarp();
+            warp_smem_sort(sbuf, N, false);
+        }
+
         int nkept = 0;
-        bool quick = thr_ok && !TF;              // cleared as soon as an irregular box shows up
+        bool screen = screen_ok;                 // cleared for good once an irregular box shows up
         for (int t0 = 0; t0 < n && nkept < cap; t0 += 32) {
             const int i = t0 + lane;
             const bool valid = i < n;
             KeyT key;
-            if (in_regs) {
-                const int r = t0 >> 5;
-                key = rk[0];
-#pragma unroll
-                for (int q = 1; q < NMS_REG_KEYS; ++q) if (r == q) key = rk[q];
-            } else {
-                key = valid ? kp[i] : KeyT::lowest();
+            if (n <= 64) key = (t0 == 0) ? key0 : key1;
+            else if (local_sort) key = valid ? sbuf[i] : KeyT::lowest();
+            else key = valid ? kp[i] : KeyT::lowest();
+            SBox<StoreT> me;
+            if (valid) me = bx[key.anchor()];
+            else { me.x0 = me.y0 = StoreT(0); me.x1 = me.y1 = StoreT(1); }
+            craw[lane] = me;
+            if (screen) {
+                const Box<IouT> mb = scale_box<StoreT, IouT>(me, sx, sy, d);
+                if (__any_sync(0xffffffffu, valid && !box_regular(mb))) screen = false;
             }
-            Box<IouT> me;
-            if (valid) me = load_box<StoreT, IouT>(bx, key.anchor(), sx, sy, d);
-            else { me.x0 = me.y0 = me.x1 = me.y1 = IouT(0); me.area = IouT(1); }
-            if (quick && __any_sync(0xffffffffu, valid && !box_regular(me))) quick = false;
-            bool alive = valid;
-
-            // against everything kept so far
-            for (int k = 0; k < nkept; ++k) {
-                if (!__any_sync(0xffffffffu, alive)) break;
-                Box<IouT> kb;
-                if (k < KS) kb = cache[k];
-                else kb = load_box<StoreT, IouT>(bx, kp[k].anchor(), sx, sy, d);
-                if (alive && suppresses<IouT, TF>(kb, me, thr, quick)) alive = false;
-            }
-
-            // among the 32 candidates of this step, in canonical order
-            tile[lane] = me;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
             __syncwarp();
-            unsigned m = __ballot_sync(0xffffffffu, alive);
-            unsigned rem = m;
-            while (rem) {
-                const int j = __ffs(rem) - 1;
-                rem &= rem - 1;
-                if (nkept + __popc(m & ((1u << j) - 1u)) >= cap) {   // box j would exceed the cap
-                    m &= (1u << j) - 1u;
-                    alive = alive && (lane < j);
-                    break;
+
+            // ---- (1) against everything kept so far: lane <-> kept box ----
+            unsigned dead = 0;                   // uniform: candidates of this step already suppressed
+            for (int k0 = 0; k0 < nkept; k0 += 32) {
+                const int k = k0 + lane;
+                unsigned mask = 0;
+                SBox<StoreT> kr;
+                if (k < nkept) {
+                    kr = (k < KS) ? kraw[k] : bx[kp[k].anchor()];
+                    if (screen) {
+#pragma unroll 8
+                        for (int c = 0; c < 32; ++c) mask |= (unsigned)(!raw_disjoint(craw[c], kr)) << c;
+                        mask &= vm & ~dead;
+                    } else {
+                        mask = vm & ~dead;
+                    }
                 }
-                Box<IouT> kb = tile[j];
-                if (lane > j && alive && suppresses<IouT, TF>(kb, me, thr, quick)) alive = false;
-                m = __ballot_sync(0xffffffffu, alive);
-                rem &= m;
+                const int npairs = enqueue(mask, (unsigned)lane);
+                for (int q0 = 0; q0 < npairs; q0 += 32) {
+                    bool s = false;
+                    unsigned c = 0;
+                    if (q0 + lane < npairs) {
+                        const unsigned pr = queue[q0 + lane];
+                        c = pr & 31u;
+                        const int kk = k0 + (int)(pr >> 5);
+                        const SBox<StoreT> kb = (kk < KS) ? kraw[kk] : bx[kp[kk].anchor()];
+                        s = decide_pair<StoreT, IouT, TF>(kb, craw[c], sx, sy, d, thr, thr_ok);
+                    }
+                    dead |= __reduce_or_sync(0xffffffffu, s ? (1u << c) : 0u);
+                }
+                __syncwarp();
+                if ((dead | ~vm) == 0xffffffffu) break;          // every candidate of the step is suppressed
             }
-            const int pos = nkept + __popc(m & lt);
-            if (alive) {
-                if (pos < KS) cache[pos] = me;
+            const bool alive = valid && !((dead >> lane) & 1u);
+            const unsigned am = vm & ~dead;
+
+            // ---- (2) pairs inside the step: which earlier candidates would suppress me ----
+            unsigned ovl = 0;
+            if (screen) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) ovl |= (unsigned)(!raw_disjoint(me, craw[j])) << j;
+                ovl &= am & lt;
+            } else {
+                ovl = am & lt;
+            }
+            if (!alive) ovl = 0;
+            sup[lane] = 0;
+            const int npairs = enqueue(ovl, (unsigned)lane);
+            for (int q0 = 0; q0 < npairs; q0 += 32) {
+                if (q0 + lane < npairs) {
+                    const unsigned pr = queue[q0 + lane];
+                    const unsigned c = pr >> 5, j = pr & 31u;
+                    if (decide_pair<StoreT, IouT, TF>(craw[j], craw[c], sx, sy, d, thr, thr_ok))
+                        atomicOr(&sup[c], 1u << j);
+                }
+            }
+            __syncwarp();
+
+            // ---- (3) greedy resolution in canonical order, up to the cap ----
+            // candidates nobody could suppress are kept outright; only the others are walked in order
+            const unsigned mysup = sup[lane];
+            const unsigned nz = __ballot_sync(0xffffffffu, mysup != 0u) & am;
+            unsigned keptm = am & ~nz;
+            for (unsigned rem = nz; rem; rem &= rem - 1) {
+                const int c = __ffs(rem) - 1;
+                const unsigned sc = __shfl_sync(0xffffffffu, mysup, c);
+                if (!(sc & keptm)) keptm |= 1u << c;      // suppressors of c are all earlier than c
+            }
+            {   // stop at the cap: keep only the first (cap - nkept) of them
+                const int room = cap - nkept;
+                const bool mine = ((keptm >> lane) & 1u) && (__popc(keptm & lt) < room);
+                keptm = __ballot_sync(0xffffffffu, mine);
+            }
+            if ((keptm >> lane) & 1u) {
+                const int pos = nkept + __popc(keptm & lt);
+                if (pos < KS) kraw[pos] = me;
                 kp[pos] = key;
             }
-            nkept += __popc(m);
+            nkept += __popc(keptm);
             __syncwarp();
         }
         if (lane == 0) kept_count[seg] = nkept;
@@ -961,7 +1080,7 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
     {
         int KS = 256;
         if (g.Kseg > 0 && g.Kseg < KS) KS = (g.Kseg + 31) & ~31;
-        size_t smem = (size_t)NMS_WARPS * (KS + 32) * sizeof(Box<IouT>);
+        size_t smem = (size_t)NMS_WARPS * ((size_t)(KS + 32) * sizeof(SBox<InT>) + (size_t)NMS_SMEM_SORT * sizeof(KeyT) + (size_t)NMS_QUEUE * sizeof(unsigned short) + 32 * sizeof(unsigned));
         int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
         if (ctas_per_sm > 12) ctas_per_sm = 12;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -1224,7 +1343,7 @@ int greedy_nms_dev(ssdc_ctx* ctx, DevCtx* d, const double* boxes, const double* 
     }
     {
         const int KS = 256;
-        size_t smem = (size_t)NMS_WARPS * (KS + 32) * sizeof(Box<double>);
+        size_t smem = (size_t)NMS_WARPS * ((size_t)(KS + 32) * sizeof(SBox<double>) + (size_t)NMS_SMEM_SORT * sizeof(Key128) + (size_t)NMS_QUEUE * sizeof(unsigned short) + 32 * sizeof(unsigned));
         LaunchScope ls(ctx, d, SSDC_K_NMS);
         SSDC_CUDA(cudaFuncSetAttribute(nms_kernel<double, double, Key128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nms_kernel<double, double, Key128, false><<<1, NMS_WARPS * 32, smem, st>>>(keys, seg_count, kept_count, lists, counters, d->boxes.as<SBox<double>>(), g, KS);
