@@ -216,6 +216,44 @@ def workload_config(args, batch, cands, note=None):
     return cfg
 
 
+def init_dist(world, local_rank, backend=None):
+    """torch.distributed is plumbing only (barrier + max over ranks); one process per GPU."""
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local_rank))
+    else:
+        dist.init_process_group(backend=backend)
+    return dist
+
+
+def max_over_ranks(x, dist):
+    """Device-timed durations are combined as the MAX over ranks."""
+    if dist is None:
+        return float(x)
+    import torch
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_throughput(world, batch_per_rank, steps, max_ms):
+    """images/s of the whole job: every rank processed batch_per_rank * steps images (weak scaling)."""
+    return world * batch_per_rank * steps / (max_ms / 1e3)
+
+
+def shard_range(total, n, i):
+    """Contiguous batch shards of ceil(total / n) images (same rule as libssdcodec's contexts)."""
+    per = (total + n - 1) // n
+    return min(total, per * i), min(total, per * (i + 1))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -226,12 +264,7 @@ def main():
         run_reference(args, rank, world)
         return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local_rank))
+    dist = init_dist(world, local_rank)
 
     from __graft_entry__ import build
     if rank == 0:
@@ -259,14 +292,6 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -281,8 +306,8 @@ def main():
     launches = ctx.launch_count() - launches0
     barrier()
     clocks = sampler.finish()
-    ms = max_over_ranks(ms)
-    value = world * B * args.steps / (ms / 1e3)
+    ms = max_over_ranks(ms, dist)
+    value = whole_job_throughput(world, B, args.steps, ms)
 
     # sanity: the step really produced detections
     counts = np.zeros(B, np.int32)
@@ -320,7 +345,7 @@ def main():
     for _ in range(e2e_steps):
         out = decode_detections(y, CONF, IOU, TOPK, 'centroids', True, 300, 300)
     dt = time.perf_counter() - t0
-    dt = max_over_ranks(dt)
+    dt = max_over_ranks(dt, dist)
     n_rows = sum(o.shape[0] for o in out if o.size)
     e2e = {'value': world * B * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(y.nbytes),
            'd2h_bytes_per_step': int(n_rows * 52 + B * 4 + 8), 'steps': e2e_steps,

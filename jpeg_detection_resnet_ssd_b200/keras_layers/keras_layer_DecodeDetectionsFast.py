@@ -7,10 +7,9 @@ from __future__ import division
 
 try:
     from .. import _lib
-    from .keras_layer_DecodeDetections import DecodeDetections as _Base
 except ImportError:
     import _lib
-    from keras_layer_DecodeDetections import DecodeDetections as _Base
+from .keras_layer_DecodeDetections import DecodeDetections as _Base
 
 
 class DecodeDetectionsFast(_Base):

@@ -3,10 +3,7 @@ height targets are `(w_gt / w_anchor) / variance` without the logarithm (referen
 line 400).  One boolean in the encode kernels."""
 from __future__ import division
 
-try:
-    from . import ssd_input_encoder as _base
-except ImportError:
-    import ssd_input_encoder as _base
+from . import ssd_input_encoder as _base
 
 DegenerateBoxError = _base.DegenerateBoxError
 

@@ -5,10 +5,7 @@ from __future__ import division
 
 import types as _types
 
-try:
-    from . import ssd_output_decoder as _base
-except ImportError:
-    import ssd_output_decoder as _base
+from . import ssd_output_decoder as _base
 
 
 def _rebind(fn):

@@ -120,3 +120,25 @@ def test_anchor_generation_matches_oracle():
     assert np.allclose(a[0], [0.013333, 0.013333, 0.1, 0.1], atol=1e-6)
     assert np.allclose(a[-1], [0.5, 0.5, 0.622254, 1.244508], atol=1e-6)
     assert e.n_boxes == [4, 6, 6, 6, 4, 4] and e.n_classes == 21
+
+
+def test_drop_in_import_paths():
+    """with the package directory first on sys.path the reference's own
+    import statements resolve to the replacements (training_dct_pascal_j2d_resnet.py:71,
+    average_precision_evaluator.py:32, inference.py:21)."""
+    import sys
+    code = (
+        "from ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder, DegenerateBoxError\n"
+        "from ssd_encoder_decoder.ssd_output_decoder import decode_detections, decode_detections_fast, greedy_nms\n"
+        "from ssd_encoder_decoder.ssd_output_decoder_no_log import decode_detections as d2\n"
+        "from ssd_encoder_decoder.ssd_input_encoder_no_log import SSDInputEncoder as E2\n"
+        "from ssd_encoder_decoder.matching_utils import match_bipartite_greedy, match_multi\n"
+        "from bounding_box_utils.bounding_box_utils import iou, convert_coordinates, intersection_area\n"
+        "from keras_layers.keras_layer_DecodeDetections import DecodeDetections\n"
+        "from keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast\n"
+        "e = SSDInputEncoder(300, 300, 20, [(38, 38), (19, 19)], scales=[0.1, 0.2, 0.3])\n"
+        "assert isinstance(e, SSDInputEncoder) and issubclass(E2, SSDInputEncoder)\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
+    assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
