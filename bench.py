@@ -121,7 +121,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.002)
 
     def finish(self):
         self._stop_evt.set()
@@ -330,8 +330,16 @@ def main():
     achieved = alg_bytes / (d1_ms / 1e3) / 1e9
     step_ms_prof = sum(v[0] for v in prof.values()) / prof_steps
     shares = {k: round(v[0] / prof_steps / step_ms_prof, 4) for k, v in prof.items() if v[1]}
-    roofline = {'bound': 'hbm', 'kernel': 'decode_filter_kernel<float,false> (D1)', 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            tj = json.load(fh)['decode_filter_tma_kernel']
+        if B == 1024 and abs(args.bg_bias - 8.0) < 1e-9:
+            traffic = tj['dram_bytes_per_launch']
+    except Exception:
+        pass
+    roofline = {'bound': 'hbm', 'kernel': 'decode_filter_tma_kernel<float,false> (D1)', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'kernel_ms': d1_ms, 'algorithmic_bytes_per_launch': alg_bytes,
                 'kernel_ms_per_step': {k: round(v[0] / prof_steps, 4) for k, v in prof.items() if v[1]},
                 'share_of_step': shares}

@@ -138,6 +138,17 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
         const unsigned u = __reduce_or_sync(0xffffffffu, mask);
         if (!u) continue;
         any |= (mask != 0);
+        const int total = __reduce_add_sync(0xffffffffu, __popc(mask));
+        if (total <= 2 * __popc(u)) {
+            // sparse: about one candidate per class present in the warp, aggregation would not save
+            // atomics - every lane reserves its own slots
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+                const int c = __ffs(mm) - 1;
+                const int pos = atomicAdd(&seg_count[(size_t)b * NS + c0 + c], 1);
+                keys[((size_t)b * NS + c0 + c) * A + pos] = KeyT::make(row[1 + c0 + c], (uint32_t)a);
+            }
+            continue;
+        }
         int mycnt = 0;
         for (unsigned uu = u; uu; uu &= uu - 1) {
             const int c = __ffs(uu) - 1;
@@ -229,53 +240,63 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Main loader: persistent CTAs, each streaming its tiles through a ring of shared-memory stages that
-// one elected thread fills with TMA bulk copies (UBLKCP) while the other warps filter the previous
-// tile.  Requires 16-byte aligned tile spans (host checks; else the LDG kernel above runs).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Main loader: persistent, warp-specialised CTAs.  One producer warp keeps a ring of shared-memory
+// stages filled with TMA bulk copies (UBLKCP) of whole-row tiles; eight consumer warps (32 rows each)
+// filter a tile as soon as its `full` mbarrier flips and hand the stage back through an `empty`
+// mbarrier.  There is no block-wide barrier: warps never wait for one another, only for data.
+// Requires 16-byte aligned tile spans (host checks; else the LDG kernel above runs).
 constexpr int D1_STAGES = 2;
+constexpr int D1_TMA_THREADS = D1_THREADS + 32;
 template <typename InT, bool FAST>
-__global__ void __launch_bounds__(D1_THREADS)
+__global__ void __launch_bounds__(D1_TMA_THREADS)
 decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int total_tiles,
                          int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
                          SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[D1_STAGES];
+    __shared__ __align__(8) uint64_t empty[D1_STAGES];
     const int W = g.W, A = g.A;
     const size_t stage_bytes = (((size_t)g.tile_rows * W * sizeof(InT)) + 127) & ~(size_t)127;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < D1_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < D1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], D1_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int t, int s) {
-        const int b = t / g.tiles, tile_id = t - b * g.tiles;
-        const int a0 = tile_id * g.tile_rows;
-        const int rows = min(g.tile_rows, A - a0);
-        const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
-        mbar_expect_tx(&full[s], bytes);
-        tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
-    };
-    if (tid == 0) {
-        for (int s = 0; s < D1_STAGES; ++s) {
-            const int t = blockIdx.x + s * gridDim.x;
-            if (t < total_tiles) issue(t, s);
+    if (warp == D1_THREADS / 32) {
+        // ---- producer warp ----
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int s = it % D1_STAGES;
+                if (it >= D1_STAGES) mbar_wait(&empty[s], (uint32_t)(((it / D1_STAGES) - 1) & 1));
+                const int b = t / g.tiles, tile_id = t - b * g.tiles;
+                const int a0 = tile_id * g.tile_rows;
+                const int rows = min(g.tile_rows, A - a0);
+                const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
+                mbar_expect_tx(&full[s], bytes);
+                tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
+            }
         }
+        return;
     }
+    // ---- consumer warps ----
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int s = it % D1_STAGES;
-        const uint32_t parity = (uint32_t)((it / D1_STAGES) & 1);
-        mbar_wait(&full[s], parity);
+        mbar_wait(&full[s], (uint32_t)((it / D1_STAGES) & 1));
         const int b = t / g.tiles, tile_id = t - b * g.tiles;
         const int a0 = tile_id * g.tile_rows;
         const int rows = min(g.tile_rows, A - a0);
         process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
                                 seg_count, keys, boxes, aux_class);
-        __syncthreads();                                   // every warp is done with stage s
-        const int tn = t + D1_STAGES * gridDim.x;
-        if (tid == 0 && tn < total_tiles) issue(tn, s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);             // this warp is done with stage s
     }
 }
 
@@ -815,7 +836,7 @@ emit_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
 // the lists l, l+32, ..; each round a warp-wide max picks the next row.  Ties between classes go
 // to the lower class id, then the lower anchor (composite key).  The lists are staged in shared
 // memory when they fit.
-constexpr int MERGE_Q = 4;            // lists per lane => up to 128 segments per image
+constexpr int MERGE_Q_MAX = 4;        // lists per lane => up to 128 segments per image
 
 template <typename KeyT> struct Comp;
 template <> struct Comp<Key64> {       // [score bits 32 | ~class 8 | ~anchor 24]
@@ -826,7 +847,12 @@ template <> struct Comp<Key64> {       // [score bits 32 | ~class 8 | ~anchor 24
     __device__ __forceinline__ static type lowest() { return 0; }
     __device__ __forceinline__ static bool gt(type a, type b) { return a > b; }
     __device__ __forceinline__ static bool eq(type a, type b) { return a == b; }
-    __device__ __forceinline__ static type shfl_xor(type a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+    __device__ __forceinline__ static type warp_max(type a) {
+        // two 32-bit REDUX steps instead of a 64-bit shuffle tree
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(a >> 32));
+        const uint32_t lo = __reduce_max_sync(0xffffffffu, ((uint32_t)(a >> 32) == hi) ? (uint32_t)a : 0u);
+        return ((uint64_t)hi << 32) | lo;
+    }
     __device__ __forceinline__ static int cls(type a) { return (int)(0xffu - (uint32_t)((a >> 24) & 0xffu)); }
     __device__ __forceinline__ static uint32_t anchor(type a) { return 0xffffffu - (uint32_t)(a & 0xffffffu); }
     __device__ __forceinline__ static double score(type a) { return (double)unord32((uint32_t)(a >> 32)); }
@@ -839,13 +865,20 @@ template <> struct Comp<Key128> {      // hi = score bits, lo = [~class 32 | ~an
     __device__ __forceinline__ static type lowest() { return Key128::lowest(); }
     __device__ __forceinline__ static bool gt(const type& a, const type& b) { return (a.hi > b.hi) || (a.hi == b.hi && a.lo > b.lo); }
     __device__ __forceinline__ static bool eq(const type& a, const type& b) { return a.hi == b.hi && a.lo == b.lo; }
-    __device__ __forceinline__ static type shfl_xor(const type& a, int m) { return shfl_xor_key(a, m); }
+    __device__ __forceinline__ static type warp_max(type best) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const type other = shfl_xor_key(best, o);
+            if (gt(other, best)) best = other;
+        }
+        return best;
+    }
     __device__ __forceinline__ static int cls(const type& a) { return (int)(0xffffffffu - (uint32_t)(a.lo >> 32)); }
     __device__ __forceinline__ static uint32_t anchor(const type& a) { return 0xffffffffu - (uint32_t)a.lo; }
     __device__ __forceinline__ static double score(const type& a) { return unord64(a.hi); }
 };
 
-template <typename StoreT, typename IouT, typename KeyT, bool SMEM>
+template <typename StoreT, typename IouT, typename KeyT, bool SMEM, int MERGE_Q>
 __global__ void __launch_bounds__(32)
 emit_merge_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
                   const int* __restrict__ out_count, const long long* __restrict__ row_offset,
@@ -923,12 +956,7 @@ emit_merge_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_co
         ck_t mine = head[0];
 #pragma unroll
         for (int q = 1; q < MERGE_Q; ++q) if (CK::gt(head[q], mine)) mine = head[q];
-        ck_t best = mine;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ck_t other = CK::shfl_xor(best, o);
-            if (CK::gt(other, best)) best = other;
-        }
+        const ck_t best = CK::warp_max(mine);
         if ((r & 31) == lane) outk = best;
         if (CK::eq(mine, best)) {                       // keys are unique: exactly one lane advances
 #pragma unroll
@@ -1024,10 +1052,10 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
             if (grid > total_tiles) grid = total_tiles;
             if (fast) {
                 SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+                decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
             } else {
                 SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+                decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
             }
             SSDC_TRY(check_launch("decode_filter_tma_kernel"));
         } else {
@@ -1120,21 +1148,24 @@ static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
     }
     const int Kcap = (g.Kseg > 0) ? min(g.Kseg, g.A) : g.A;
     LaunchScope ls(ctx, d, SSDC_K_MERGE);
-    if (g.NS <= 32 * MERGE_Q && g.A < (1 << 24) && g.C <= 256) {
+    if (g.NS <= 32 * MERGE_Q_MAX && g.A < (1 << 24) && g.C <= 256) {
         // warp-per-image k-way merge
         const size_t list_bytes = may_sort ? (size_t)g.NS * Kcap * sizeof(KeyT) : 0;
         const bool use_smem = g.NS > 1 && list_bytes > 0 && list_bytes <= 100 * 1024;
-        if (use_smem) {
-            SSDC_CUDA(cudaFuncSetAttribute(emit_merge_kernel<InT, IouT, KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)list_bytes));
-            emit_merge_kernel<InT, IouT, KeyT, true><<<(unsigned)B, 32, list_bytes, d->stream>>>(
+        auto launch = [&](auto kern) -> int {
+            if (use_smem) SSDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)list_bytes));
+            kern<<<(unsigned)B, 32, use_smem ? list_bytes : 0, d->stream>>>(
                 d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
                 d->boxes.as<SBox<InT>>(), fast ? d->aux_class.as<int>() : nullptr, g, Kcap,
                 d->out_rows.as<double>(), d->out_anchor.as<int>());
+            return SSDC_OK;
+        };
+        if (g.NS <= 32) {
+            if (use_smem) SSDC_TRY(launch(emit_merge_kernel<InT, IouT, KeyT, true, 1>));
+            else SSDC_TRY(launch(emit_merge_kernel<InT, IouT, KeyT, false, 1>));
         } else {
-            emit_merge_kernel<InT, IouT, KeyT, false><<<(unsigned)B, 32, 0, d->stream>>>(
-                d->keys.as<KeyT>(), ints + L.kept_count, d->out_count.as<int>(), d->row_offset.as<long long>(),
-                d->boxes.as<SBox<InT>>(), fast ? d->aux_class.as<int>() : nullptr, g, Kcap,
-                d->out_rows.as<double>(), d->out_anchor.as<int>());
+            if (use_smem) SSDC_TRY(launch(emit_merge_kernel<InT, IouT, KeyT, true, MERGE_Q_MAX>));
+            else SSDC_TRY(launch(emit_merge_kernel<InT, IouT, KeyT, false, MERGE_Q_MAX>));
         }
         SSDC_TRY(check_launch("emit_merge_kernel"));
         return SSDC_OK;
