@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "ctx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ssdc {
 
@@ -41,6 +42,7 @@ struct DecodeArgs {
     int do_nms, K, Kseg, always_sort;
     double iou_thr, sx, sy, d;
     int nseg;
+    int sweep;      // per-image candidate lists with composite keys (image sweep path)
 };
 
 // ---------------------------------------------------------------------------
@@ -138,6 +140,29 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
         const unsigned u = __reduce_or_sync(0xffffffffu, mask);
         if (!u) continue;
         any |= (mask != 0);
+        if (sizeof(InT) == 4 && g.sweep) {
+            // image sweep path: one candidate list per image, keys carry the class
+            // [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one atomic per warp
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&seg_count[b], tot);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long* ck = reinterpret_cast<unsigned long long*>(keys) + (size_t)b * NS * A + base + (incl - cnt);
+            for (unsigned mm = mask; mm; mm &= mm - 1) {
+                const int c = __ffs(mm) - 1;
+                *ck++ = ((unsigned long long)ord32((float)row[1 + c0 + c]) << 32) |
+                        ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
+                        (unsigned long long)(0xffffffu - (unsigned)a);
+            }
+            continue;
+        }
         const int total = __reduce_add_sync(0xffffffffu, __popc(mask));
         if (total <= 2 * __popc(u)) {
             // sparse: about one candidate per class present in the warp, aggregation would not save
@@ -691,6 +716,338 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 }
 
 // ---------------------------------------------------------------------------
+// S: image sweep (decode_detections with a finite top_k; the hot configuration).
+//
+// Per-class greedy NMS followed by a cross-class top-k (ssd_output_decoder.py:205-221) equals one
+// sweep over ALL candidates of the image in descending (score, then class, then anchor) order in
+// which a candidate is only compared with kept boxes of its own class, stopped as soon as top_k
+// boxes are kept: later candidates have lower scores, so they can neither enter the top-k nor
+// influence a higher-scored decision.  Only the needed prefix of the candidate list is ever
+// selected (radix select), sorted and examined, independent of how many candidates the threshold
+// let through.  One CTA per image:
+//   select : 8-bit radix passes over the image's candidate keys pick a score threshold that yields
+//            the next <= 1024 best candidates; they are compacted into shared memory and sorted;
+//   sweep  : 32 candidates per step; the eight warps screen them against the kept boxes of the same
+//            class (lane <-> kept box, raw-corner disjointness), overlapping pairs are decided in
+//            batches (exact, division-free), warp 0 resolves the step and appends to the kept list.
+// ---------------------------------------------------------------------------
+constexpr int SW_THREADS = 256;
+constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_CHUNK = 1024;          // candidates staged + sorted at a time
+constexpr int SW_TARGET = 448;          // the selection aims at >= this many (and <= SW_CHUNK)
+constexpr int SW_KMAX = 512;            // largest top_k the sweep path handles
+constexpr int SW_QUEUE = 1024;          // per-warp pair queue (16-bit entries)
+
+__device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu - (unsigned)((k >> 24) & 0xffu)); }
+__device__ __forceinline__ unsigned ck_anchor(unsigned long long k) { return 0xffffffu - (unsigned)(k & 0xffffffu); }
+
+template <typename IouT, bool TF>
+__global__ void __launch_bounds__(SW_THREADS)
+sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
+             const SBox<float>* __restrict__ boxes, DecodeArgs g,
+             unsigned long long* __restrict__ final_keys, int* __restrict__ out_count) {
+    __shared__ unsigned long long ck[SW_CHUNK];                  // current chunk, sorted descending
+    __shared__ unsigned long long kkey[SW_KMAX];                 // kept keys in keep order
+    __shared__ SBox<float> kraw[SW_KMAX];                        // their raw corners
+    __shared__ unsigned char kcls[SW_KMAX];
+    __shared__ SBox<float> craw[32];
+    __shared__ unsigned char ccls[32];
+    __shared__ unsigned cmask[256];                              // per class: candidates of the step
+    __shared__ unsigned sup[32];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned short queue[SW_WARPS][SW_QUEUE];
+    __shared__ unsigned s_dead, s_vm, s_cnt, s_screen_off;
+    __shared__ int s_nkept;
+    __shared__ unsigned long long s_tau, s_hi;
+    __shared__ int s_done;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = g.K;
+    const int n = img_count[b];
+    const unsigned long long* gk = keys + (size_t)b * img_stride;
+    const SBox<float>* bx = boxes + (size_t)b * g.A;
+    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
+    const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
+    const bool screen_ok = thr_ok && g.sx > 0.0 && g.sy > 0.0 && !TF;
+    const unsigned lt = (1u << lane) - 1u;
+
+    if (tid == 0) { s_nkept = 0; s_hi = ~0ull; s_screen_off = 0; s_done = 0; }
+    for (int i = tid; i < 256; i += SW_THREADS) cmask[i] = 0;
+    __syncthreads();
+    if (n == 0) { if (tid == 0) out_count[b] = 0; return; }
+
+    // warp-local helper: lane's set bits of `mask` become queue entries (a << 5 | bit)
+    unsigned short* myq = queue[warp];
+    auto enqueue = [&](unsigned mask, unsigned a) -> int {
+        const int np = __popc(mask);
+        int start = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, start, o);
+            if (lane >= o) start += v;
+        }
+        const int npairs = __shfl_sync(0xffffffffu, start, 31);
+        start -= np;
+        for (unsigned rem = mask; rem; rem &= rem - 1)
+            myq[start++] = (unsigned short)((a << 5) | (unsigned)(__ffs(rem) - 1));
+        __syncwarp();
+        return npairs;
+    };
+
+    int remaining = n;                      // candidates with key < s_hi
+    while (true) {
+        // ------------------------------------------------------------ select the next chunk
+        const unsigned long long hi = s_hi;
+        unsigned long long tau = 0;
+        if (remaining > SW_CHUNK) {
+            unsigned long long prefix = 0;          // decided high bits of the threshold
+            unsigned long long pmask = 0;           // which bits are decided
+            int above = 0;                          // candidates above the bucket being refined
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                for (int i = tid; i < 256; i += SW_THREADS) hist[i] = 0;
+                __syncthreads();
+                for (int i = tid; i < n; i += SW_THREADS) {
+                    const unsigned long long k = gk[i];
+                    if (k < hi && (k & pmask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int cum = above, dsel = 0;
+                    for (int dg = 255; dg >= 0; --dg) {
+                        if (cum + (int)hist[dg] >= SW_TARGET || dg == 0) { dsel = dg; break; }
+                        cum += (int)hist[dg];
+                    }
+                    // dsel: bucket in which the SW_TARGET-th best candidate lies
+                    s_cnt = (unsigned)cum;                        // strictly above the bucket
+                    s_tau = prefix | ((unsigned long long)dsel << shift);
+                    s_done = (cum + (int)hist[dsel] <= SW_CHUNK) || shift == 0;
+                }
+                __syncthreads();
+                prefix = s_tau;
+                pmask |= 0xffull << shift;
+                above = (int)s_cnt;
+                const int fin = s_done;
+                __syncthreads();
+                if (fin) break;
+            }
+            tau = prefix;                               // lower edge of the selected bucket
+        }
+        // compact {tau <= key < hi} into shared memory
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += SW_THREADS) {
+            const int i = i0 + tid;
+            const unsigned long long k = (i < n) ? gk[i] : 0ull;
+            const bool take = (i < n) && k >= tau && k < hi;
+            const unsigned m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (take) ck[base + __popc(m & lt)] = k;
+            }
+        }
+        __syncthreads();
+        const int cn = (int)s_cnt;
+        {
+            const int N = pow2_ceil(cn > 1 ? cn : 1);
+            for (int i = cn + tid; i < N; i += SW_THREADS) ck[i] = 0ull;
+            __syncthreads();
+            for (int k2 = 2; k2 <= N; k2 <<= 1) {
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < (N >> 1); i += SW_THREADS) {
+                        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                        const int hi2 = lo | j;
+                        const unsigned long long a = ck[lo], c2 = ck[hi2];
+                        const bool desc = (lo & k2) == 0;
+                        if (desc ? (c2 > a) : (a > c2)) { ck[lo] = c2; ck[hi2] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+
+        // ------------------------------------------------------------ sweep the chunk
+        for (int t0 = 0; t0 < cn; t0 += 32) {
+            int nkept = s_nkept;
+            if (nkept >= K) break;
+            // candidates of this step
+            unsigned long long key = 0;
+            bool valid = false;
+            SBox<float> me;
+            me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
+            int mycls = 0;
+            if (warp == 0) {
+                valid = t0 + lane < cn;
+                if (valid) {
+                    key = ck[t0 + lane];
+                    mycls = ck_cls(key);
+                    me = bx[ck_anchor(key)];
+                    atomicOr(&cmask[mycls], 1u << lane);
+                }
+                craw[lane] = me;
+                ccls[lane] = (unsigned char)mycls;
+                if (screen_ok && !s_screen_off) {
+                    const Box<IouT> mb = scale_box<float, IouT>(me, sx, sy, d);
+                    if (__any_sync(0xffffffffu, valid && !box_regular(mb))) { if (lane == 0) s_screen_off = 1; }
+                }
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                if (lane == 0) { s_vm = vm; s_dead = 0; }
+            }
+            __syncthreads();
+            const bool screen = screen_ok && !s_screen_off;
+            const unsigned vm = s_vm;
+
+            // (1) kept boxes of the same class: warp w takes kept boxes w*32.., lane <-> kept box
+            for (int k0 = warp * 32; k0 < nkept; k0 += SW_THREADS) {
+                const int k = k0 + lane;
+                unsigned mask = 0;
+                if (k < nkept) {
+                    unsigned cand = cmask[kcls[k]] & vm;
+                    if (screen) {
+                        const SBox<float> kr = kraw[k];
+                        for (unsigned rem = cand; rem; rem &= rem - 1) {
+                            const int c = __ffs(rem) - 1;
+                            if (raw_disjoint(craw[c], kr)) cand &= ~(1u << c);
+                        }
+                    }
+                    mask = cand;
+                }
+                const int npairs = enqueue(mask, (unsigned)lane);
+                for (int q0 = 0; q0 < npairs; q0 += 32) {
+                    bool sres = false;
+                    unsigned c = 0;
+                    if (q0 + lane < npairs) {
+                        const unsigned pr = myq[q0 + lane];
+                        c = pr & 31u;
+                        const int kk = k0 + (int)(pr >> 5);
+                        sres = decide_pair<float, IouT, TF>(kraw[kk], craw[c], sx, sy, d, thr, thr_ok);
+                    }
+                    const unsigned dm = __reduce_or_sync(0xffffffffu, sres ? (1u << c) : 0u);
+                    if (dm && lane == 0) atomicOr(&s_dead, dm);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+
+            // (2)+(3) inside the step, warp 0
+            if (warp == 0) {
+                const unsigned dead = s_dead;
+                const bool alive = valid && !((dead >> lane) & 1u);
+                const unsigned am = vm & ~dead;
+                unsigned ovl = 0;
+                if (alive) {
+                    ovl = cmask[mycls] & am & lt;
+                    if (screen) {
+                        for (unsigned rem = ovl; rem; rem &= rem - 1) {
+                            const int j = __ffs(rem) - 1;
+                            if (raw_disjoint(me, craw[j])) ovl &= ~(1u << j);
+                        }
+                    }
+                }
+                sup[lane] = 0;
+                const int npairs = enqueue(ovl, (unsigned)lane);
+                for (int q0 = 0; q0 < npairs; q0 += 32) {
+                    if (q0 + lane < npairs) {
+                        const unsigned pr = myq[q0 + lane];
+                        const unsigned c = pr >> 5, j = pr & 31u;
+                        if (decide_pair<float, IouT, TF>(craw[j], craw[c], sx, sy, d, thr, thr_ok))
+                            atomicOr(&sup[c], 1u << j);
+                    }
+                }
+                __syncwarp();
+                const unsigned mysup = sup[lane];
+                const unsigned nz = __ballot_sync(0xffffffffu, mysup != 0u) & am;
+                unsigned keptm = am & ~nz;
+                for (unsigned rem = nz; rem; rem &= rem - 1) {
+                    const int c = __ffs(rem) - 1;
+                    const unsigned sc = __shfl_sync(0xffffffffu, mysup, c);
+                    if (!(sc & keptm)) keptm |= 1u << c;
+                }
+                {
+                    const int room = K - nkept;
+                    const bool mine = ((keptm >> lane) & 1u) && (__popc(keptm & lt) < room);
+                    keptm = __ballot_sync(0xffffffffu, mine);
+                }
+                if ((keptm >> lane) & 1u) {
+                    const int pos = nkept + __popc(keptm & lt);
+                    kraw[pos] = me;
+                    kcls[pos] = (unsigned char)mycls;
+                    kkey[pos] = key;
+                }
+                if (valid) cmask[mycls] = 0;            // clear for the next step
+                if (lane == 0) s_nkept = nkept + __popc(keptm);
+            }
+            __syncthreads();
+        }
+        const int nkept = s_nkept;
+        remaining -= cn;
+        if (nkept >= K || remaining <= 0 || cn == 0) break;
+        if (tid == 0) s_hi = tau;
+        __syncthreads();
+    }
+
+    // ------------------------------------------------------------ final order
+    const int nkept = s_nkept;
+    unsigned long long* fk = final_keys + (size_t)b * K;
+    if (nkept >= K || g.always_sort) {
+        // truncated (or layer mode): descending score, the sweep order
+        for (int i = tid; i < nkept; i += SW_THREADS) fk[i] = kkey[i];
+    } else {
+        // nothing truncated: classes ascending, inside a class the keep order (:212-218)
+        for (int i = tid; i < nkept; i += SW_THREADS) {
+            const int c = kcls[i];
+            int pos = 0;
+            for (int j = 0; j < nkept; ++j) {
+                const int cj = kcls[j];
+                pos += (cj < c) || (cj == c && j < i);
+            }
+            fk[pos] = kkey[i];
+        }
+    }
+    if (tid == 0) out_count[b] = nkept;
+}
+
+// exclusive scan of per-image row counts -> packed row offsets (single CTA)
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int* __restrict__ out_count, int B, long long* __restrict__ row_offset) {
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        const long long c = (b < B) ? out_count[b] : 0;
+        long long x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long yv = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += yv;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long yv = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += yv;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? warp_sums[warp - 1] : 0) + (x - c);
+        if (b < B) row_offset[b] = before;
+        __syncthreads();
+        if (tid == 1023) carry = before + c;
+        __syncthreads();
+    }
+    if (tid == 0) row_offset[B] = carry;
+}
+
+// ---------------------------------------------------------------------------
 // D4: per-image totals + scan, cross-class top-k, row output
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -754,6 +1111,22 @@ __device__ __forceinline__ void write_row(double* __restrict__ rows, int* __rest
     o[4] = (double)((IouT)s.x1 * sx);
     o[5] = (double)((IouT)s.y1 * sy);
     anchors[r] = (int)anchor;
+}
+
+template <typename IouT>
+__global__ void __launch_bounds__(64)
+sweep_emit_kernel(const unsigned long long* __restrict__ final_keys, const int* __restrict__ out_count,
+                  const long long* __restrict__ row_offset, const SBox<float>* __restrict__ boxes, DecodeArgs g,
+                  double* __restrict__ rows, int* __restrict__ anchors) {
+    const int b = blockIdx.x;
+    const int cnt = out_count[b];
+    const long long off = row_offset[b];
+    const SBox<float>* bx = boxes + (size_t)b * g.A;
+    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy;
+    for (int r = threadIdx.x; r < cnt; r += 64) {
+        const unsigned long long k = final_keys[(size_t)b * g.K + r];
+        write_row<float, IouT>(rows, anchors, off + r, ck_cls(k), (double)unord32((uint32_t)(k >> 32)), ck_anchor(k), bx, sx, sy);
+    }
 }
 
 constexpr int EMIT_THREADS = 256;
@@ -1002,6 +1375,73 @@ static IntLayout int_layout(size_t nseg) {
     return L;
 }
 
+template <typename InT>
+static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B, InT thr, bool fast,
+                     int* seg_count, typename KeyOf<InT>::type* keys, SBox<InT>* boxes, int* aux) {
+    cudaStream_t st = d->stream;
+    constexpr int V = 16 / (int)sizeof(InT);
+    LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
+    const size_t row_bytes = (size_t)g.W * sizeof(InT);
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (((size_t)g.A * row_bytes) % 16 == 0) &&
+                        (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
+    if (tma_ok) {
+        const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
+        const size_t smem = stage_bytes * D1_STAGES;
+        int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (ctas_per_sm > 4) ctas_per_sm = 4;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const long long total_tiles = (long long)B * g.tiles;
+        long long grid = (long long)d->sm_count * ctas_per_sm;
+        if (grid > total_tiles) grid = total_tiles;
+        if (fast) {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+        } else {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+        }
+        SSDC_TRY(check_launch("decode_filter_tma_kernel"));
+    } else {
+        size_t smem = (((size_t)g.tile_rows * g.W + V) * sizeof(InT) + 15) & ~(size_t)15;
+        dim3 grid((unsigned)((size_t)B * g.tiles));
+        if (fast) {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_kernel<InT, true><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+        } else {
+            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_filter_kernel<InT, false><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
+        }
+        SSDC_TRY(check_launch("decode_filter_kernel"));
+    }
+    return SSDC_OK;
+}
+
+// Image sweep path (decode_detections / DecodeDetections layer with a finite top_k, float32 input).
+template <typename InT, typename IouT, bool TF>
+static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B, InT thr) {
+    if (sizeof(InT) != 4) { set_error("internal: sweep path needs float32 input"); return SSDC_ERR_STATE; }
+    typedef typename KeyOf<InT>::type KeyT;
+    IntLayout L = int_layout((size_t)g.nseg);
+    int* ints = d->ints.as<int>();
+    int* img_count = ints + L.seg_count;            // one counter per image (first B entries)
+    cudaStream_t st = d->stream;
+    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, false, img_count, d->keys.as<KeyT>(), d->boxes.as<SBox<InT>>(), nullptr));
+    SSDC_TRY(d->merge_scratch.ensure((size_t)B * g.K * sizeof(unsigned long long)));
+    {
+        LaunchScope ls(ctx, d, SSDC_K_NMS);
+        sweep_kernel<IouT, TF><<<(unsigned)B, SW_THREADS, 0, st>>>(
+            d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
+            d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
+        SSDC_TRY(check_launch("sweep_kernel"));
+    }
+    {
+        LaunchScope ls(ctx, d, SSDC_K_MERGE);
+        scan_counts_kernel<<<1, 1024, 0, st>>>(d->out_count.as<int>(), (int)B, d->row_offset.as<long long>());
+        SSDC_TRY(check_launch("scan_counts_kernel"));
+    }
+    return SSDC_OK;
+}
+
 template <typename InT, typename IouT, bool TF>
 static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B,
                         double conf_thresh, int cmp_f32_rn) {
@@ -1032,45 +1472,11 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
     }
 
     SSDC_CUDA(cudaMemsetAsync(ints, 0, (L.kept_count) * sizeof(int), st));
+    if (g.sweep) return run_sweep<InT, IouT, TF>(ctx, d, y_dev, g, B, thr);
     const int n1 = SORT_BYTES1 / (int)sizeof(KeyT), n2 = SORT_BYTES2 / (int)sizeof(KeyT), n3 = SORT_BYTES3 / (int)sizeof(KeyT);
 
     // D1
-    {
-        constexpr int V = 16 / (int)sizeof(InT);
-        LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
-        const size_t row_bytes = (size_t)g.W * sizeof(InT);
-        const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (((size_t)g.A * row_bytes) % 16 == 0) &&
-                            (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
-        if (tma_ok) {
-            const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
-            const size_t smem = stage_bytes * D1_STAGES;
-            int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
-            if (ctas_per_sm > 4) ctas_per_sm = 4;
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
-            const long long total_tiles = (long long)B * g.tiles;
-            long long grid = (long long)d->sm_count * ctas_per_sm;
-            if (grid > total_tiles) grid = total_tiles;
-            if (fast) {
-                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
-            } else {
-                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
-            }
-            SSDC_TRY(check_launch("decode_filter_tma_kernel"));
-        } else {
-            size_t smem = (((size_t)g.tile_rows * g.W + V) * sizeof(InT) + 15) & ~(size_t)15;
-            dim3 grid((unsigned)((size_t)B * g.tiles));
-            if (fast) {
-                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_kernel<InT, true><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
-            } else {
-                SSDC_CUDA(cudaFuncSetAttribute(decode_filter_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                decode_filter_kernel<InT, false><<<grid, D1_THREADS, smem, st>>>(y_dev, g, thr, seg_count, keys, boxes, aux);
-            }
-            SSDC_TRY(check_launch("decode_filter_kernel"));
-        }
-    }
+    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, fast, seg_count, keys, boxes, aux));
     // plan
     {
         LaunchScope ls(ctx, d, SSDC_K_PLAN);
@@ -1148,6 +1554,13 @@ static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
     }
     const int Kcap = (g.Kseg > 0) ? min(g.Kseg, g.A) : g.A;
     LaunchScope ls(ctx, d, SSDC_K_MERGE);
+    if (g.sweep) {
+        sweep_emit_kernel<IouT><<<(unsigned)B, 64, 0, d->stream>>>(
+            d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>(), d->row_offset.as<long long>(),
+            reinterpret_cast<const SBox<float>*>(d->boxes.p), g, d->out_rows.as<double>(), d->out_anchor.as<int>());
+        SSDC_TRY(check_launch("sweep_emit_kernel"));
+        return SSDC_OK;
+    }
     if (g.NS <= 32 * MERGE_Q_MAX && g.A < (1 << 24) && g.C <= 256) {
         // warp-per-image k-way merge
         const size_t list_bytes = may_sort ? (size_t)g.NS * Kcap * sizeof(KeyT) : 0;
@@ -1209,6 +1622,9 @@ static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* 
     g.tiles = (int)((job.A + rows - 1) / rows);
     // float32 input stays float32 end to end only where the reference never upcasts:
     // input_coords == 'corners' (ssd_output_decoder.py:186-190) and the Keras layers.
+    // image sweep path: per-class semantics with a finite top_k that no per-class cap can undercut
+    g.sweep = (job.dtype == SSDC_F32) && !fast && g.K > 0 && g.K <= SW_KMAX && job.C <= 256 && job.A < (1 << 24) &&
+              (!layer || p.nms_cap >= p.top_k) && getenv("SSDC_NO_SWEEP") == nullptr;
     *iou_f32 = (job.dtype == SSDC_F32) && (layer || p.input_coords == SSDC_COORDS_CORNERS);
     *tf = layer;
     *cmp_rn = *iou_f32;

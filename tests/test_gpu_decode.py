@@ -214,3 +214,25 @@ def test_debug_decoder_and_layers(ctx):
     assert sum(nb) == 8732
     layers = dec.get_pred_layers(d, nb)
     assert all(0 <= l < 6 for ls in layers for l in ls)
+
+
+@pytest.mark.parametrize('layout,bias,thr', [('ssd300', 8.0, 0.01), ('ssd300', 6.0, 0.01), ('ssd512', 6.0, 0.001), ('tiny', 1.0, 0.05)])
+def test_image_sweep_equals_per_class_pipeline(layout, bias, thr, ctx):
+    """The image-sweep path (one descending sweep over all candidates of an image, stop at top_k) and
+    the general per-class pipeline (sort + NMS per (image, class) + k-way merge) are two
+    implementations of the same function: identical rows, bit for bit."""
+    import os
+    enc = synth.make_encoder(SSDInputEncoder, layout)
+    kw = synth.layout_kwargs(layout)
+    C = kw['n_classes'] + 1
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 3, 77, bg_bias=bias, hot=40)
+    for top_k in (200, 7):
+        a = _lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, top_k, 'centroids', True, kw['img_height'], kw['img_width'], 'half', ctx=ctx)
+        os.environ['SSDC_NO_SWEEP'] = '1'
+        try:
+            b = _lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, top_k, 'centroids', True, kw['img_height'], kw['img_width'], 'half', ctx=ctx)
+        finally:
+            del os.environ['SSDC_NO_SWEEP']
+        ra, ca = product_rows7(*a)
+        rb, cb = product_rows7(*b)
+        assert np.array_equal(ca, cb) and np.array_equal(ra, rb)
