@@ -733,8 +733,8 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 // ---------------------------------------------------------------------------
 constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_CHUNK = 1024;          // candidates staged + sorted at a time
-constexpr int SW_TARGET = 448;          // the selection aims at >= this many (and <= SW_CHUNK)
+constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
+constexpr int SW_TARGET = 288;          // the selection aims at >= this many (and <= SW_CHUNK)
 constexpr int SW_KMAX = 512;            // largest top_k the sweep path handles
 constexpr int SW_QUEUE = 1024;          // per-warp pair queue (16-bit entries)
 
@@ -812,16 +812,32 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
                     if (k < hi && (k & pmask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int cum = above, dsel = 0;
-                    for (int dg = 255; dg >= 0; --dg) {
-                        if (cum + (int)hist[dg] >= SW_TARGET || dg == 0) { dsel = dg; break; }
-                        cum += (int)hist[dg];
+                if (warp == 0) {
+                    // walk the 256 buckets from the top with one warp: lane l owns buckets [8l, 8l+8)
+                    int mine = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) mine += (int)hist[lane * 8 + q];
+                    int suffix = mine;                       // sum over lanes >= this lane
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+                        if (lane + o < 32) suffix += v;
                     }
-                    // dsel: bucket in which the SW_TARGET-th best candidate lies
-                    s_cnt = (unsigned)cum;                        // strictly above the bucket
-                    s_tau = prefix | ((unsigned long long)dsel << shift);
-                    s_done = (cum + (int)hist[dsel] <= SW_CHUNK) || shift == 0;
+                    const int cum_before = above + suffix - mine;     // candidates above this lane's buckets
+                    const bool has = (cum_before < SW_TARGET) && (cum_before + mine >= SW_TARGET);
+                    const unsigned hm = __ballot_sync(0xffffffffu, has);
+                    if (hm ? has : (lane == 0)) {            // (no lane: fewer than SW_TARGET left -> take everything)
+                        int cum = cum_before, dsel = lane * 8;
+                        for (int q = 7; q >= 0; --q) {
+                            const int h = (int)hist[lane * 8 + q];
+                            if (cum + h >= SW_TARGET || q == 0) { dsel = lane * 8 + q; break; }
+                            cum += h;
+                        }
+                        // dsel: bucket in which the SW_TARGET-th best candidate lies
+                        s_cnt = (unsigned)cum;                        // strictly above the bucket
+                        s_tau = prefix | ((unsigned long long)dsel << shift);
+                        s_done = (cum + (int)hist[dsel] <= SW_CHUNK) || shift == 0;
+                    }
                 }
                 __syncthreads();
                 prefix = s_tau;
