@@ -34,14 +34,14 @@ struct ssdc_encoder {
     double variances[4];
     int64_t bad_image = -1;
     // per device of the context
-    struct PerDev { ssdc::Buf anchor_box, anchor_tail; };
+    struct PerDev { ssdc::Buf anchor_box, anchor_tail, anchor_boxf; };
     std::vector<PerDev> dev;
 };
 
 namespace ssdc {
 
 constexpr int E1_THREADS = 256;
-constexpr int E1_PER_THREAD = 4;
+constexpr int E1_PER_THREAD = 8;
 constexpr int E1_CHUNK = E1_THREADS * E1_PER_THREAD;
 constexpr int E3_THREADS = 128;
 constexpr int E3_ROWS = 128;
@@ -50,7 +50,11 @@ struct GtPrep {
     double data[4];     // target coordinates in the encoder's `coords` format (written to y_encoded)
     Box<double> box;    // corner form + union area term, as `iou` sees it
     int cls;
-    int pad;
+    int regular;        // finite, positive area term
+    float4 sf;          // float32 screening box (corners rounded outward; NaN when irregular)
+    float w_up, h_up;   // upper bounds of the side lengths
+    float area_lo;      // lower bound of the area term
+    float pad;
 };
 
 struct EncArgs {
@@ -97,15 +101,46 @@ __device__ __forceinline__ void encode_offsets(const double* t, const double* a,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Exact shortcuts for the ground-truth x anchor IoU (both boxes "regular": finite, area term > 0):
+//   disjoint boxes                      => iou == +0 exactly;
+//   iou <= min(a1, a2) / max(a1, a2)    (inter <= smaller area, union >= larger area), so a pair
+//   whose area ratio is below a bound (with a 2^-40 guard for the roundings) is below that bound.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool regular_d(const Box<double>& b) { return b.area > 0.0 && b.area < INFINITY; }
+__device__ __forceinline__ bool disjoint_d(const Box<double>& a, const Box<double>& b) {
+    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
+}
+__device__ __forceinline__ bool ratio_below(const Box<double>& a, const Box<double>& b, double bound_lo) {
+    const double mn = a.area < b.area ? a.area : b.area;
+    const double mx = a.area < b.area ? b.area : a.area;
+    return mn < bound_lo * mx;
+}
+constexpr double GUARD_LO = 1.0 - 0x1p-40;
+
+// float32 screening box: the corners rounded OUTWARD, so that float-disjoint implies double-disjoint.
+// An irregular box becomes NaN: every comparison fails and the pair takes the exact path.
+__device__ __forceinline__ float4 screen_box(const Box<double>& b) {
+    float4 f;
+    if (!regular_d(b)) { f.x = f.y = f.z = f.w = __int_as_float(0x7fc00000); return f; }
+    f.x = __double2float_rd(b.x0); f.y = __double2float_rd(b.y0);
+    f.z = __double2float_ru(b.x1); f.w = __double2float_ru(b.y1);
+    return f;
+}
+__device__ __forceinline__ bool screen_disjoint(const float4& a, const float4& b) {
+    return (a.z <= b.x) || (b.z <= a.x) || (a.w <= b.y) || (b.w <= a.y);
+}
+
 __global__ void anchor_prep_kernel(const double* __restrict__ anchors, int A, int coords, double d, int log_wh,
                                    double v0, double v1, double v2, double v3,
-                                   Box<double>* __restrict__ abox, double* __restrict__ tail) {
+                                   Box<double>* __restrict__ abox, double* __restrict__ tail, float4* __restrict__ aboxf) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= A) return;
     double c4[4] = {anchors[4 * a], anchors[4 * a + 1], anchors[4 * a + 2], anchors[4 * a + 3]};
     double x0, y0, x1, y1;
     to_corners(c4, coords, &x0, &y0, &x1, &y1);
     abox[a] = make_box<double>(x0, y0, x1, y1, d);
+    aboxf[a] = screen_box(abox[a]);
     double v[4] = {v0, v1, v2, v3};
     double o[4];
     encode_offsets(c4, c4, v, coords, log_wh, o);      // an unmatched row encodes the anchor against itself
@@ -139,97 +174,181 @@ __global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, 
     to_corners(p.data, g.coords, &x0, &y0, &x1, &y1);
     p.box = make_box<double>(x0, y0, x1, y1, g.d);
     p.cls = (int)r[0];
-    p.pad = 0;
+    p.regular = regular_d(p.box) ? 1 : 0;
+    p.sf = screen_box(p.box);
+    p.w_up = __fsub_ru(p.sf.z, p.sf.x);
+    p.h_up = __fsub_ru(p.sf.w, p.sf.y);
+    p.area_lo = __double2float_rd(p.box.area);
+    p.pad = 0.f;
     out[i] = p;
 }
-
-// ---------------------------------------------------------------------------
-// Exact shortcuts for the ground-truth x anchor IoU (both boxes "regular": finite, area term > 0):
-//   disjoint boxes                      => iou == +0 exactly;
-//   iou <= min(a1, a2) / max(a1, a2)    (inter <= smaller area, union >= larger area), so a pair
-//   whose area ratio is below a bound (with a 2^-40 guard for the roundings) is below that bound.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ bool regular_d(const Box<double>& b) { return b.area > 0.0 && b.area < INFINITY; }
-__device__ __forceinline__ bool disjoint_d(const Box<double>& a, const Box<double>& b) {
-    return (a.x1 <= b.x0) || (b.x1 <= a.x0) || (a.y1 <= b.y0) || (b.y1 <= a.y0);
-}
-__device__ __forceinline__ bool ratio_below(const Box<double>& a, const Box<double>& b, double bound_lo) {
-    const double mn = a.area < b.area ? a.area : b.area;
-    const double mx = a.area < b.area ? b.area : a.area;
-    return mn < bound_lo * mx;
-}
-constexpr double GUARD_LO = 1.0 - 0x1p-40;
 
 // ---------------------------------------------------------------------------
 // E1: per GT row, best anchor inside one chunk of anchors
 // ---------------------------------------------------------------------------
 constexpr int E1_GROUP = 64;      // GT rows reduced per block-level pass
 
-__global__ void __launch_bounds__(E1_THREADS)
+constexpr int E1_ROWS = 4;          // GT rows screened per barrier round
+
+__global__ void __launch_bounds__(E1_THREADS, 4)
 rowbest_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
-               const Box<double>* __restrict__ abox, EncArgs g,
-               double* __restrict__ part_val, int* __restrict__ part_idx, int* __restrict__ irregular) {
-    __shared__ double s_val[E1_THREADS / 32][E1_GROUP];
-    __shared__ int s_idx[E1_THREADS / 32][E1_GROUP];
-    const int chunk = blockIdx.x % g.chunks;
-    const int b = blockIdx.x / g.chunks;
+               const Box<double>* __restrict__ abox, const float4* __restrict__ aboxf, EncArgs g, int B, int chunk_hi,
+               double* __restrict__ part_val, int* __restrict__ part_idx, int* __restrict__ irregular,
+               unsigned long long* __restrict__ rowmax_bits) {
+    // E1_ROWS GT rows per round: (A) every thread screens its anchors against the rows with cheap
+    // float32 tests - disjointness of the outward-rounded boxes (then iou == +0 exactly) and the shape
+    // bound against the best IoU already known for the row - and queues the surviving (row, anchor)
+    // pairs in shared memory; (B) the survivors are evaluated exactly (float64) with all threads busy
+    // and reduced per row with np.argmax semantics.  Two barriers per round.
+    __shared__ unsigned short queue[E1_ROWS * E1_CHUNK];      // row << 13 | anchor inside the chunk
+    __shared__ int s_qn[2];
+    __shared__ double s_pv[E1_ROWS][E1_THREADS / 32];
+    __shared__ int s_pi[E1_ROWS][E1_THREADS / 32];
+    __shared__ int s_first;
+    // chunk-major launch order, LAST chunk first: the large anchors of the late predictor layers give
+    // large ground-truth boxes a high IoU early, which lets the small-anchor chunks skip almost all
+    // of their pairs through the shape bound
+    const int chunk = chunk_hi - (int)(blockIdx.x / B);
+    const int b = blockIdx.x % B;
     const long long g0 = gt_off[b], g1 = gt_off[b + 1];
     const int m = (int)(g1 - g0);
     if (m == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a_base = chunk * E1_CHUNK;
 
-    Box<double> ab[E1_PER_THREAD];
-    int ai[E1_PER_THREAD];
-    bool areg[E1_PER_THREAD];
+    float4 af[E1_PER_THREAD];
+    float aarea[E1_PER_THREAD];             // lower bound of the area term
+    int first = 0x7fffffff;                 // lowest regular anchor index of this thread
+    unsigned validm = 0;                    // which of this thread's anchors exist
 #pragma unroll
     for (int k = 0; k < E1_PER_THREAD; ++k) {
-        ai[k] = a_base + k * E1_THREADS + tid;
-        areg[k] = false;
-        if (ai[k] < g.A) { ab[k] = abox[ai[k]]; areg[k] = regular_d(ab[k]); }
+        const int a = a_base + k * E1_THREADS + tid;
+        if (a < g.A) validm |= 1u << k;
+        aarea[k] = 0.f;
+        af[k].x = af[k].y = af[k].z = af[k].w = __int_as_float(0x7fc00000);
+        if (a < g.A) {
+            af[k] = aboxf[a];
+            if (af[k].x == af[k].x) {
+                if (first == 0x7fffffff) first = a;
+                aarea[k] = __double2float_rd(abox[a].area);
+            }
+        }
     }
+    if (tid == 0) { s_first = 0x7fffffff; s_qn[0] = 0; s_qn[1] = 0; }
+    __syncthreads();
+    {
+        const int wf = __reduce_min_sync(0xffffffffu, first);
+        if (lane == 0 && wf != 0x7fffffff) atomicMin(&s_first, wf);
+    }
+    __syncthreads();
+    const int first_reg = s_first;
     bool irr = false;
-    for (int r0 = 0; r0 < m; r0 += E1_GROUP) {
-        const int rn = min(E1_GROUP, m - r0);
-        for (int rr = 0; rr < rn; ++rr) {
-            const Box<double> gb = gtp[g0 + r0 + rr].box;
-            const bool greg = regular_d(gb);
-            double bv = -INFINITY;
-            int bi = 0x7fffffff;
+    int round = 0;
+    for (int r0 = 0; r0 < m; r0 += E1_ROWS, ++round) {
+        const int rn = min(E1_ROWS, m - r0);
+        int* qn = &s_qn[round & 1];
+        // ---- (A) screening
+        unsigned keepm[E1_ROWS];
+        int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < E1_PER_THREAD; ++k) {
-                if (ai[k] < g.A) {
-                    double s;
-                    if (greg && areg[k]) {
-                        if (disjoint_d(gb, ab[k])) s = 0.0;
-                        else if (bv > 0.0 && ratio_below(gb, ab[k], bv * GUARD_LO)) continue;   // cannot reach the running best
-                        else s = iou_boxes<double>(gb, ab[k]);
-                    } else {
-                        s = iou_boxes<double>(gb, ab[k]);
-                        irr |= (s < 0.0);
+        for (int q = 0; q < E1_ROWS; ++q) {
+            keepm[q] = 0;
+            if (q < rn) {
+                const GtPrep* gp = gtp + g0 + r0 + q;
+                const float4 gf = gp->sf;
+                const bool greg = gp->regular != 0;
+                const double best = __longlong_as_double((long long)rowmax_bits[g0 + r0 + q]);
+                const float cut = __fmul_rd(__double2float_rd(best), 1.0f - 0x1p-20f);
+                const float gw = gp->w_up, gh = gp->h_up, garea = gp->area_lo;
+                unsigned km = 0;
+#pragma unroll
+                for (int k = 0; k < E1_PER_THREAD; ++k) {
+                    // (anchors past the end and irregular ones carry NaN screening boxes: never disjoint)
+                    bool keep = !screen_disjoint(gf, af[k]);                      // disjoint: iou == +0 exactly
+                    if (greg && cut > 0.f) {
+                        // shape bound: inter <= min(w) * min(h) whatever the positions, so
+                        // iou <= mwh / (a1 + a2 - mwh); below the row's known best => neither argmax nor tie
+                        const float mwh = __fmul_ru(fminf(gw, __fsub_ru(af[k].z, af[k].x)), fminf(gh, __fsub_ru(af[k].w, af[k].y)));
+                        const float den = __fsub_rd(__fadd_rd(garea, aarea[k]), mwh);
+                        if (den > 0.f && mwh < __fmul_rd(cut, den) && af[k].x == af[k].x) keep = false;   // division-free
                     }
-                    if (better(s, ai[k], bv, bi)) { bv = s; bi = ai[k]; }
+                    km |= (unsigned)keep << k;
                 }
+                keepm[q] = km & validm;
+                cnt += __popc(keepm[q]);
             }
+        }
+        if (__any_sync(0xffffffffu, cnt != 0)) {
+            int incl = cnt;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            if (lane == 0) { s_val[warp][rr] = bv; s_idx[warp][rr] = bi; }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(qn, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+#pragma unroll
+            for (int q = 0; q < E1_ROWS; ++q)
+                for (unsigned mm = keepm[q]; mm; mm &= mm - 1)
+                    queue[base++] = (unsigned short)((q << 13) | ((__ffs(mm) - 1) * E1_THREADS + tid));
         }
         __syncthreads();
+        // ---- (B) exact evaluation of the survivors
+        const int nq = *qn;
+        double bv[E1_ROWS];
+        int bi[E1_ROWS];
+#pragma unroll
+        for (int q = 0; q < E1_ROWS; ++q) { bv[q] = -INFINITY; bi[q] = 0x7fffffff; }
+        for (int i = tid; i < nq; i += E1_THREADS) {
+            const unsigned e = queue[i];
+            const int q = (int)(e >> 13);
+            const int a = a_base + (int)(e & 0x1fffu);
+            const GtPrep* gp = gtp + g0 + r0 + q;
+            const Box<double> gb = gp->box;
+            const Box<double> ab = abox[a];
+            double s;
+            if (gp->regular && regular_d(ab)) {
+                if (disjoint_d(gb, ab)) s = 0.0;
+                else s = iou_boxes<double>(gb, ab);
+            } else {
+                s = iou_boxes<double>(gb, ab);
+                irr |= (s < 0.0);
+            }
+#pragma unroll
+            for (int qq = 0; qq < E1_ROWS; ++qq)
+                if (qq == q && better(s, a, bv[qq], bi[qq])) { bv[qq] = s; bi[qq] = a; }
+        }
+        if (nq > 0) {
+#pragma unroll
+            for (int q = 0; q < E1_ROWS; ++q) {
+                if (__any_sync(0xffffffffu, bi[q] != 0x7fffffff)) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(0xffffffffu, bv[q], o);
+                        int oi = __shfl_xor_sync(0xffffffffu, bi[q], o);
+                        if (better(ov, oi, bv[q], bi[q])) { bv[q] = ov; bi[q] = oi; }
+                    }
+                }
+                if (lane == 0) { s_pv[q][warp] = bv[q]; s_pi[q][warp] = bi[q]; }
+            }
+        }
+        __syncthreads();
+        // ---- (C) combine with the +0 baseline of the screened-out (regular) pairs
         if (tid < rn) {
-            double bv = s_val[0][tid];
-            int bi = s_idx[0][tid];
+            const GtPrep* gp = gtp + g0 + r0 + tid;
+            double rv = -INFINITY; int ri = 0x7fffffff;
+            if (gp->regular && first_reg != 0x7fffffff) { rv = 0.0; ri = first_reg; }
+            if (nq > 0) {
 #pragma unroll
-            for (int w = 1; w < E1_THREADS / 32; ++w)
-                if (better(s_val[w][tid], s_idx[w][tid], bv, bi)) { bv = s_val[w][tid]; bi = s_idx[w][tid]; }
-            part_val[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = bv;
-            part_idx[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = bi;
+                for (int w = 0; w < E1_THREADS / 32; ++w)
+                    if (better(s_pv[tid][w], s_pi[tid][w], rv, ri)) { rv = s_pv[tid][w]; ri = s_pi[tid][w]; }
+            }
+            part_val[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = rv;
+            part_idx[(size_t)(g0 + r0 + tid) * g.chunks + chunk] = ri;
+            if (rv > 0.0) atomicMax(&rowmax_bits[g0 + r0 + tid], (unsigned long long)__double_as_longlong(rv));
         }
-        __syncthreads();
+        if (tid == 0) *qn = 0;
     }
     if (__any_sync(0xffffffffu, irr) && lane == 0) atomicOr(&irregular[b], 1);
 }
@@ -277,7 +396,7 @@ match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
              const Box<double>* __restrict__ abox, EncArgs g,
              double* __restrict__ part_val, int* __restrict__ part_idx,
              const int* __restrict__ irregular, int* __restrict__ match) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_val[E2_THREADS / 32];
     __shared__ int red_idx[E2_THREADS / 32];
     __shared__ int s_asel;
@@ -363,6 +482,59 @@ match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
 // ---------------------------------------------------------------------------
 // E3: per-anchor matching + offsets + write-out
 // ---------------------------------------------------------------------------
+// Decision for one anchor: which ground-truth row it is matched to (-1: none) and whether it is
+// neutral.  `sgt` / `smatch`: the image's GT boxes and bipartite matches in shared memory.
+__device__ __forceinline__ void decide_anchor(int a, int m, const Box<double>* sgt, const float4* sgf, const int* smatch,
+                                              bool all_gt_regular,
+                                              const Box<double>* __restrict__ abox, const float4* __restrict__ aboxf,
+                                              const EncArgs& g, bool prune, double prune_lo, int* gsel_out, bool* neutral_out) {
+    int gsel = -1;
+    bool neutral = false;
+    if (m > 0) {
+        // bipartite assignment: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (last write wins)
+        int bip = -1;
+        for (int r = 0; r < m; ++r) if (smatch[r] == a) bip = r;
+        // column of the similarity matrix; a bipartite column is all zeros (ssd_input_encoder.py:366)
+        double cv = -INFINITY; int cg = 0x7fffffff;
+        if (bip >= 0) { cv = 0.0; cg = 0; }
+        else {
+            const float4 af = aboxf[a];
+            const bool areg = af.x == af.x;              // screen boxes of irregular anchors are NaN
+            if (areg && all_gt_regular) {
+                // regular pairs: iou >= 0, screened-out pairs exactly +0 => start at (0, row 0)
+                cv = 0.0; cg = 0;
+                Box<double> ab;
+                bool have_ab = false;
+                for (int r = 0; r < m; ++r) {
+                    if (screen_disjoint(sgf[r], af)) continue;
+                    if (!have_ab) { ab = abox[a]; have_ab = true; }
+                    const Box<double> gb = sgt[r];
+                    if (disjoint_d(gb, ab)) continue;
+                    if (prune && ratio_below(gb, ab, prune_lo)) continue;        // below both thresholds
+                    const double s = iou_boxes<double>(gb, ab);
+                    if (better(s, r, cv, cg)) { cv = s; cg = r; }
+                }
+            } else {
+                const Box<double> ab = abox[a];
+                for (int r = 0; r < m; ++r) {
+                    const double s = iou_boxes<double>(sgt[r], ab);
+                    if (better(s, r, cv, cg)) { cv = s; cg = r; }
+                }
+            }
+        }
+        gsel = bip;
+        bool zeroed = bip >= 0;
+        if (g.multi && (cv >= g.pos_thr)) {      // matching_utils.py:109-114, ssd_input_encoder.py:375-381
+            gsel = cg;
+            zeroed = true;
+        }
+        const double rest = zeroed ? 0.0 : cv;   // np.amax of the column after the zeroing
+        neutral = rest >= g.neg_thr;              // ssd_input_encoder.py:388-390
+    }
+    *gsel_out = gsel;
+    *neutral_out = neutral;
+}
+
 struct RowMeta {
     double off[4];
     int cls;        // class column set to 1, or -1 for none (neutral background)
@@ -371,12 +543,12 @@ struct RowMeta {
 
 __global__ void __launch_bounds__(E3_THREADS)
 write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
-             const Box<double>* __restrict__ abox, const double* __restrict__ tail,
+             const Box<double>* __restrict__ abox, const float4* __restrict__ aboxf, const double* __restrict__ tail,
              const int* __restrict__ match, EncArgs g, int tiles,
              double* __restrict__ y, double* __restrict__ y2, int* __restrict__ midx) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     RowMeta* meta = reinterpret_cast<RowMeta*>(smem_raw);               // E3_ROWS
-    Box<double>* sgt = reinterpret_cast<Box<double>*>(meta + E3_ROWS);   // the image's GT boxes
+    float4* sgf = reinterpret_cast<float4*>(meta + E3_ROWS);             // the image's GT boxes: screening form
     const int tile = blockIdx.x % tiles;
     const int b = blockIdx.x / tiles;
     const int a0 = tile * E3_ROWS;
@@ -385,9 +557,15 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
     const int m = (int)(gt_off[b + 1] - g0);
     const int tid = threadIdx.x;
 
+    Box<double>* sgt = reinterpret_cast<Box<double>*>(sgf + m);          // ... and exact form
     int* smatch = reinterpret_cast<int*>(sgt + m);
-    for (int r = tid; r < m; r += E3_THREADS) { sgt[r] = gtp[g0 + r].box; smatch[r] = match[g0 + r]; }
-    __syncthreads();
+    bool greg_local = true;
+    for (int r = tid; r < m; r += E3_THREADS) {
+        const Box<double> gb = gtp[g0 + r].box;
+        sgt[r] = gb; sgf[r] = screen_box(gb); smatch[r] = match[g0 + r];
+        greg_local = greg_local && regular_d(gb);
+    }
+    const bool all_gt_regular = __syncthreads_and(greg_local) != 0;
 
     // pairs whose IoU is certainly below both thresholds never influence a decision (they can be
     // neither a match nor make the anchor neutral, nor be the argmax among pairs that do)
@@ -397,40 +575,8 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
 
     if (tid < rows) {
         const int a = a0 + tid;
-        int gsel = -1;
-        bool neutral = false;
-        if (m > 0) {
-            const Box<double> ab = abox[a];
-            const bool areg = regular_d(ab);
-            // bipartite assignment: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (last write wins)
-            int bip = -1;
-            for (int r = 0; r < m; ++r) if (smatch[r] == a) bip = r;
-            // column of the similarity matrix; a bipartite column is all zeros (ssd_input_encoder.py:366)
-            double cv = -INFINITY; int cg = 0x7fffffff;
-            if (bip >= 0) { cv = 0.0; cg = 0; }
-            else {
-                for (int r = 0; r < m; ++r) {
-                    const Box<double> gb = sgt[r];
-                    double s;
-                    if (areg && regular_d(gb)) {
-                        if (disjoint_d(gb, ab)) s = 0.0;
-                        else if (prune && ratio_below(gb, ab, prune_lo)) s = 0.0;   // stands for "below thr_min"
-                        else s = iou_boxes<double>(gb, ab);
-                    } else {
-                        s = iou_boxes<double>(gb, ab);
-                    }
-                    if (better(s, r, cv, cg)) { cv = s; cg = r; }
-                }
-            }
-            gsel = bip;
-            bool zeroed = bip >= 0;
-            if (g.multi && (cv >= g.pos_thr)) {      // matching_utils.py:109-114, ssd_input_encoder.py:375-381
-                gsel = cg;
-                zeroed = true;
-            }
-            const double rest = zeroed ? 0.0 : cv;   // np.amax of the column after the zeroing
-            neutral = rest >= g.neg_thr;              // ssd_input_encoder.py:388-390
-        }
+        int gsel; bool neutral;
+        decide_anchor(a, m, sgt, sgf, smatch, all_gt_regular, abox, aboxf, g, prune, prune_lo, &gsel, &neutral);
         RowMeta mt;
         const double* t = tail + (size_t)a * 12;
         if (gsel >= 0) {
@@ -500,6 +646,101 @@ write_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
     }
 }
 
+// ---- E3, main path: rows are assembled in shared memory and the whole tile leaves with ONE TMA
+// bulk store (cp.async.bulk shared -> global, SASS UBLKCP / UTMASTG class), no per-element index
+// arithmetic.  Needs 16-byte aligned tiles (host checks; else write_kernel above).
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(E3_THREADS)
+write_tma_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+                 const Box<double>* __restrict__ abox, const float4* __restrict__ aboxf, const double* __restrict__ tail,
+                 const int* __restrict__ match, EncArgs g, int tiles,
+                 double* __restrict__ y, double* __restrict__ y2, int* __restrict__ midx) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = g.W, C = g.C;
+    double* trow = reinterpret_cast<double*>(smem_raw);                                   // E3_ROWS x W
+    float4* sgf = reinterpret_cast<float4*>(trow + (size_t)E3_ROWS * W);
+    const int tile = blockIdx.x % tiles;
+    const int b = blockIdx.x / tiles;
+    const int a0 = tile * E3_ROWS;
+    const int rows = min(E3_ROWS, g.A - a0);
+    const long long g0 = gt_off[b];
+    const int m = (int)(gt_off[b + 1] - g0);
+    const int tid = threadIdx.x;
+    Box<double>* sgt = reinterpret_cast<Box<double>*>(sgf + m);          // ... and exact form
+    int* smatch = reinterpret_cast<int*>(sgt + m);
+    bool greg_local = true;
+    for (int r = tid; r < m; r += E3_THREADS) {
+        const Box<double> gb = gtp[g0 + r].box;
+        sgt[r] = gb; sgf[r] = screen_box(gb); smatch[r] = match[g0 + r];
+        greg_local = greg_local && regular_d(gb);
+    }
+    const bool all_gt_regular = __syncthreads_and(greg_local) != 0;
+
+    const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
+    const bool prune = thr_min > 0.0 && thr_min < INFINITY;
+    const double prune_lo = thr_min * GUARD_LO;
+
+    if (tid < rows) {
+        const int a = a0 + tid;
+        int gsel; bool neutral;
+        decide_anchor(a, m, sgt, sgf, smatch, all_gt_regular, abox, aboxf, g, prune, prune_lo, &gsel, &neutral);
+        double* row = trow + (size_t)tid * W;
+        const double* t = tail + (size_t)a * 12;
+        double off[4];
+        int cls;
+        if (gsel >= 0) {
+            const GtPrep gp = gtp[g0 + gsel];
+            double an[4] = {t[4], t[5], t[6], t[7]};
+            double v[4] = {t[8], t[9], t[10], t[11]};
+            encode_offsets(gp.data, an, v, g.coords, g.log_wh, off);
+            cls = gp.cls;
+            if (neutral && gp.cls == g.background_id) cls = -1;
+        } else {
+            off[0] = t[0]; off[1] = t[1]; off[2] = t[2]; off[3] = t[3];
+            cls = neutral ? -1 : g.background_id;
+        }
+        for (int c = 0; c < C; ++c) row[c] = 0.0;
+        if (cls >= 0) row[cls] = 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) row[C + k] = off[k];
+#pragma unroll
+        for (int k = 4; k < 12; ++k) row[C + k] = t[k];
+        if (midx) midx[(size_t)b * g.A + a] = (gsel >= 0) ? gsel : (neutral ? -2 : -1);
+    }
+    // generic-proxy writes to shared memory must be visible to the async proxy before the bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const size_t base = ((size_t)b * g.A + a0) * W;
+    const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(double));
+    if (tid == 0) {
+        tma_store_1d(y + base, trow, bytes);
+        tma_store_commit_wait_read();
+    }
+    if (y2) {
+        // diagnostics copy (ssd_input_encoder.py:412-416): same rows with the four offsets zeroed
+        __syncthreads();
+        if (tid < rows) {
+            double* row = trow + (size_t)tid * W;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) row[C + k] = 0.0;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(y2 + base, trow, bytes);
+            tma_store_commit_wait_read();
+        }
+    }
+}
+
 static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, int64_t* n_gt) {
     const int64_t first = gt_offsets[b0], last = gt_offsets[b0 + B];
     const int64_t n = last - first;
@@ -510,7 +751,7 @@ static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int
     for (int64_t i = 0; i <= B; ++i) h[i] = gt_offsets[b0 + i] - first;
     SSDC_CUDA(cudaMemcpyAsync(d->gt_off.p, h, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->stream));
     if (n > 0) {
-        SSDC_TRY(d->gt.ensure((size_t)n * 5 * sizeof(double) + (size_t)n * sizeof(GtPrep)));
+        SSDC_TRY(d->gt.ensure((((size_t)n * 5 * sizeof(double) + 63) & ~(size_t)63) + (size_t)n * sizeof(GtPrep)));
         SSDC_CUDA(cudaMemcpyAsync(d->gt.p, gt + first * 5, (size_t)n * 5 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     }
     return SSDC_OK;
@@ -541,7 +782,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     GtPrep* gtp = nullptr;
     int* match = nullptr;
     if (n_gt > 0) {
-        gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (size_t)n_gt * 5 * sizeof(double));
+        gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (((size_t)n_gt * 5 * sizeof(double) + 63) & ~(size_t)63));
         // scratch: partials (val, idx), row bests, taken columns, done flags, matches, irregular flags
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -549,13 +790,16 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         size_t o_pi = carve((size_t)n_gt * g.chunks * sizeof(int));
         size_t o_mt = carve((size_t)n_gt * sizeof(int));
         size_t o_ir = carve((size_t)B * sizeof(int));
+        size_t o_rm = carve((size_t)n_gt * sizeof(unsigned long long));
         SSDC_TRY(d->partial.ensure(off));
         char* base = d->partial.as<char>();
         double* part_val = reinterpret_cast<double*>(base + o_pv);
         int* part_idx = reinterpret_cast<int*>(base + o_pi);
         match = reinterpret_cast<int*>(base + o_mt);
         int* irregular = reinterpret_cast<int*>(base + o_ir);
+        unsigned long long* rowmax_bits = reinterpret_cast<unsigned long long*>(base + o_rm);
         SSDC_CUDA(cudaMemsetAsync(irregular, 0, (size_t)B * sizeof(int), st));
+        SSDC_CUDA(cudaMemsetAsync(rowmax_bits, 0, (size_t)n_gt * sizeof(unsigned long long), st));
         {
             LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
             gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
@@ -563,8 +807,15 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         }
         {
             LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
-            rowbest_kernel<<<(unsigned)(B * g.chunks), E1_THREADS, 0, st>>>(gtp, gt_off, abox, g, part_val, part_idx, irregular);
+            // the last chunk (largest anchors) first, in its own launch: its results seed the per-row best
+            // IoU that lets every other chunk discard most pairs with the shape bound
+            rowbest_kernel<<<(unsigned)B, E1_THREADS, 0, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), g, (int)B, g.chunks - 1, part_val, part_idx, irregular, rowmax_bits);
             SSDC_TRY(check_launch("rowbest_kernel"));
+            if (g.chunks > 1) {
+                ctx->launches.fetch_add(1, std::memory_order_relaxed);
+                rowbest_kernel<<<(unsigned)(B * (g.chunks - 1)), E1_THREADS, 0, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), g, (int)B, g.chunks - 2, part_val, part_idx, irregular, rowmax_bits);
+                SSDC_TRY(check_launch("rowbest_kernel"));
+            }
         }
         {
             LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
@@ -576,10 +827,21 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     }
     {
         const int tiles = (int)((enc->A + E3_ROWS - 1) / E3_ROWS);
-        size_t smem = sizeof(RowMeta) * E3_ROWS + (size_t)max_m * (sizeof(Box<double>) + sizeof(int)) + 16;
+        const size_t row_bytes = (size_t)g.W * sizeof(double);
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
+                            (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)E3_ROWS * row_bytes) % 16 == 0) &&
+                            ((((size_t)enc->A % E3_ROWS) * row_bytes) % 16 == 0);
+        const size_t smem_tma = (size_t)E3_ROWS * row_bytes + (size_t)max_m * (sizeof(Box<double>) + sizeof(float4) + sizeof(int)) + 16;
         LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+        if (tma_ok && smem_tma <= 200 * 1024) {
+            SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+            write_tma_kernel<<<(unsigned)(B * tiles), E3_THREADS, smem_tma, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
+            SSDC_TRY(check_launch("write_tma_kernel"));
+            return SSDC_OK;
+        }
+        size_t smem = sizeof(RowMeta) * E3_ROWS + (size_t)max_m * (sizeof(Box<double>) + sizeof(float4) + sizeof(int)) + 16;
         SSDC_CUDA(cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        write_kernel<<<(unsigned)(B * tiles), E3_THREADS, smem, st>>>(gtp, gt_off, abox, tail, match, g, tiles, y_dev, y2_dev, midx_dev);
+        write_kernel<<<(unsigned)(B * tiles), E3_THREADS, smem, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
         SSDC_TRY(check_launch("write_kernel"));
     }
     return SSDC_OK;
@@ -611,18 +873,19 @@ int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const d
         if (cudaSetDevice(d.device) != cudaSuccess) r = SSDC_ERR_CUDA;
         if (r == SSDC_OK) r = enc->dev[i].anchor_box.ensure((size_t)A * sizeof(Box<double>));
         if (r == SSDC_OK) r = enc->dev[i].anchor_tail.ensure((size_t)A * 12 * sizeof(double));
+        if (r == SSDC_OK) r = enc->dev[i].anchor_boxf.ensure((size_t)A * sizeof(float4));
         if (r == SSDC_OK) r = d.t0buf.ensure((size_t)A * 4 * sizeof(double));
         if (r == SSDC_OK && cudaMemcpyAsync(d.t0buf.p, anchors, (size_t)A * 4 * sizeof(double), cudaMemcpyHostToDevice, d.stream) != cudaSuccess) r = SSDC_ERR_CUDA;
         if (r == SSDC_OK) {
             LaunchScope ls(ctx, &d, SSDC_K_THIN);
             anchor_prep_kernel<<<(unsigned)((A + 127) / 128), 128, 0, d.stream>>>(
                 d.t0buf.as<double>(), (int)A, p->coords, dd, p->log_wh, variances[0], variances[1], variances[2], variances[3],
-                enc->dev[i].anchor_box.as<Box<double>>(), enc->dev[i].anchor_tail.as<double>());
+                enc->dev[i].anchor_box.as<Box<double>>(), enc->dev[i].anchor_tail.as<double>(), enc->dev[i].anchor_boxf.as<float4>());
             r = check_launch("anchor_prep_kernel");
         }
         if (r == SSDC_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) { set_error("anchor_prep failed: %s", cudaGetErrorString(cudaGetLastError())); r = SSDC_ERR_CUDA; }
         if (r != SSDC_OK) {
-            for (auto& pd : enc->dev) { pd.anchor_box.release(); pd.anchor_tail.release(); }
+            for (auto& pd : enc->dev) { pd.anchor_box.release(); pd.anchor_tail.release(); pd.anchor_boxf.release(); }
             delete enc;
             return r;
         }
@@ -638,6 +901,7 @@ void ssdc_encoder_destroy(ssdc_encoder* enc) {
         cudaSetDevice(enc->ctx->devs[i].device);
         enc->dev[i].anchor_box.release();
         enc->dev[i].anchor_tail.release();
+        enc->dev[i].anchor_boxf.release();
     }
     delete enc;
 }
