@@ -412,6 +412,71 @@ def extra_numbers(ctx, _lib, enc, peak):
             'kernel_ms': {k: round(v[0] / 3, 4) for k, v in prof.items() if v[1]},
         }
         ctx.dev_free(d_out)
+
+    # BASELINE configs[4] in miniature on one GPU: encode -> decode_detections_fast round trip, the
+    # float64 y_encoded never leaves the device (every positive confidence is exactly 1.0)
+    B = 512
+    gt = synth.synth_ground_truth(300, 300, 20, B, seed=78)
+    flat, offs = synth.flatten_ground_truth(gt)
+    d_enc = ctx.dev_alloc(B * A_SSD300 * 33 * 8)
+    pf = _lib.DecodeParams()
+    pf.mode, pf.input_coords, pf.normalize, pf.border_pixels = _lib.MODE_FAST, 0, 1, 0
+    pf.top_k, pf.nms_cap, pf.log_wh, pf.do_nms = 0, 0, 1, 1
+    pf.conf_thresh, pf.iou_thresh, pf.img_h, pf.img_w = 0.5, 0.45, 300.0, 300.0
+
+    def roundtrip():
+        _lib.check(lib.ssdc_encode(h, _lib.ptr(flat), _lib.ptr(offs), B, 1, d_enc, None, None))
+        _lib.check(lib.ssdc_decode_submit(ctx.handle, d_enc, _lib.F64, 1, B, A_SSD300, N_CLASSES, _lib.C.byref(pf)))
+    for _ in range(3):
+        roundtrip()
+    ctx.synchronize()
+    steps = 5
+    ctx.timer_start()
+    for _ in range(steps):
+        roundtrip()
+    ms = ctx.timer_stop()
+    counts = np.zeros(B, np.int32)
+    total = _lib.C.c_int64(0)
+    rc = lib.ssdc_decode_collect(ctx.handle, None, 0, _lib.ptr(counts), None, _lib.C.byref(total))
+    n_gt = int(offs[-1])
+    out['roundtrip_encode_decode_fast_b512'] = {
+        'images_per_s': B * steps / (ms / 1e3), 'ms_per_step': ms / steps,
+        'ground_truth_boxes': n_gt, 'decoded_boxes': int(total.value),
+        'note': 'device-resident float64 y_encoded; top_k=all so rows are emitted at collect time (not timed)'}
+    ctx.dev_free(d_enc)
+
+    # BASELINE configs[3]: SSD512 layout (24564 anchors), conf 0.001, dense candidates, B = 512
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    enc512 = synth.make_encoder(SSDInputEncoder, 'ssd512')
+    a512 = synth.anchors_of(enc512)
+    A = a512.shape[0]
+    uniq = 32
+    base = synth.synth_y_pred(a512, enc512.variances, N_CLASSES, uniq, 4321, bg_bias=6.0, hot=40)
+    B = 512
+    d_y = ctx.dev_alloc(B * A * 33 * 4)
+    for i in range(0, B, uniq):
+        _lib.check(lib.ssdc_memcpy_h2d(ctx.handle, 0, _lib.C.c_void_p(d_y.value + i * A * 33 * 4), _lib.ptr(base), base.nbytes))
+    p5 = decode_params(_lib)
+    p5.conf_thresh, p5.img_h, p5.img_w = 0.001, 512.0, 512.0
+    for _ in range(3):
+        _lib.check(lib.ssdc_decode_submit(ctx.handle, d_y, _lib.F32, 1, B, A, N_CLASSES, _lib.C.byref(p5)))
+    ctx.synchronize()
+    ctx.timer_start()
+    for _ in range(steps):
+        _lib.check(lib.ssdc_decode_submit(ctx.handle, d_y, _lib.F32, 1, B, A, N_CLASSES, _lib.C.byref(p5)))
+    ms = ctx.timer_stop()
+    ctx.profile_enable(True)
+    for _ in range(3):
+        _lib.check(lib.ssdc_decode_submit(ctx.handle, d_y, _lib.F32, 1, B, A, N_CLASSES, _lib.C.byref(p5)))
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    d1 = prof['decode_filter'][0] / max(prof['decode_filter'][1], 1)
+    out['decode_ssd512_dense_b512'] = {
+        'images_per_s': B * steps / (ms / 1e3), 'ms_per_step': ms / steps,
+        'candidates_per_image': float((base[:, :, 1:N_CLASSES] > 0.001).sum()) / uniq,
+        'decode_filter_ms': d1, 'decode_filter_frac_of_hbm_peak': B * A * 33 * 4 / (d1 / 1e3) / 1e9 / peak,
+        'kernel_ms': {k: round(v[0] / 3, 4) for k, v in prof.items() if v[1]}}
+    ctx.dev_free(d_y)
     return out
 
 
