@@ -735,7 +735,7 @@ constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
 constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
 constexpr int SW_TARGET = 288;          // the selection aims at >= this many (and <= SW_CHUNK)
-constexpr int SW_KMAX = 512;            // largest top_k the sweep path handles
+constexpr int SW_KMAX = 256;            // largest top_k the sweep path handles
 constexpr int SW_QUEUE = 1024;          // per-warp pair queue (16-bit entries)
 
 __device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu - (unsigned)((k >> 24) & 0xffu)); }
@@ -750,6 +750,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
     __shared__ unsigned long long kkey[SW_KMAX];                 // kept keys in keep order
     __shared__ SBox<float> kraw[SW_KMAX];                        // their raw corners
     __shared__ unsigned char kcls[SW_KMAX];
+    __shared__ SBox<float> cbox[SW_CHUNK];                       // raw corners of the whole chunk (prefetched)
     __shared__ SBox<float> craw[32];
     __shared__ unsigned char ccls[32];
     __shared__ unsigned cmask[256];                              // per class: candidates of the step
@@ -885,33 +886,40 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         }
 
         // ------------------------------------------------------------ sweep the chunk
+        // all candidate boxes of the chunk are fetched up front (one L2 round trip for the CTA instead
+        // of one per step on the critical path)
+        for (int i = tid; i < cn; i += SW_THREADS) cbox[i] = bx[ck_anchor(ck[i])];
+        __syncthreads();
+        // warp 0 owns the step state: lane <-> candidate.  `stage` publishes a step's candidates
+        unsigned long long key = 0;
+        bool valid = false;
+        SBox<float> me;
+        me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
+        int mycls = 0;
+        auto stage = [&](int t0) {
+            valid = t0 + lane < cn;
+            key = 0; mycls = 0;
+            me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
+            if (valid) {
+                key = ck[t0 + lane];
+                mycls = ck_cls(key);
+                me = cbox[t0 + lane];
+                atomicOr(&cmask[mycls], 1u << lane);
+            }
+            craw[lane] = me;
+            ccls[lane] = (unsigned char)mycls;
+            if (screen_ok && !s_screen_off) {
+                const Box<IouT> mb = scale_box<float, IouT>(me, sx, sy, d);
+                if (__any_sync(0xffffffffu, valid && !box_regular(mb))) { if (lane == 0) s_screen_off = 1; }
+            }
+            const unsigned vmm = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) { s_vm = vmm; s_dead = 0; }
+        };
+        if (warp == 0 && cn > 0) stage(0);
+        __syncthreads();
         for (int t0 = 0; t0 < cn; t0 += 32) {
             int nkept = s_nkept;
             if (nkept >= K) break;
-            // candidates of this step
-            unsigned long long key = 0;
-            bool valid = false;
-            SBox<float> me;
-            me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
-            int mycls = 0;
-            if (warp == 0) {
-                valid = t0 + lane < cn;
-                if (valid) {
-                    key = ck[t0 + lane];
-                    mycls = ck_cls(key);
-                    me = bx[ck_anchor(key)];
-                    atomicOr(&cmask[mycls], 1u << lane);
-                }
-                craw[lane] = me;
-                ccls[lane] = (unsigned char)mycls;
-                if (screen_ok && !s_screen_off) {
-                    const Box<IouT> mb = scale_box<float, IouT>(me, sx, sy, d);
-                    if (__any_sync(0xffffffffu, valid && !box_regular(mb))) { if (lane == 0) s_screen_off = 1; }
-                }
-                const unsigned vm = __ballot_sync(0xffffffffu, valid);
-                if (lane == 0) { s_vm = vm; s_dead = 0; }
-            }
-            __syncthreads();
             const bool screen = screen_ok && !s_screen_off;
             const unsigned vm = s_vm;
 
@@ -993,7 +1001,10 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
                     kkey[pos] = key;
                 }
                 if (valid) cmask[mycls] = 0;            // clear for the next step
-                if (lane == 0) s_nkept = nkept + __popc(keptm);
+                const int nk2 = nkept + __popc(keptm);
+                if (lane == 0) s_nkept = nk2;
+                __syncwarp();
+                if (t0 + 32 < cn && nk2 < K) stage(t0 + 32);
             }
             __syncthreads();
         }
