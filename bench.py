@@ -209,7 +209,8 @@ def workload_config(args, batch, cands, note=None):
            'batch_per_gpu': batch, 'anchors': A_SSD300, 'classes': N_CLASSES,
            'candidates_per_image': round(cands, 1), 'bg_bias': args.bg_bias,
            'unique_images': min(args.unique, batch),
-           'l2': 'input per step (%.0f MB) exceeds the 126 MB L2; no flush needed' % (batch * A_SSD300 * 33 * 4 / 1e6),
+           'l2': ('input per step (%.0f MB) exceeds the 126 MB L2; no flush needed' % (batch * A_SSD300 * 33 * 4 / 1e6))
+                 if batch * A_SSD300 * 33 * 4 > 126e6 else 'n/a (host arm)',
            'parallelism': 'batch shards, one process per GPU, no collective'}
     if note:
         cfg['note'] = note
