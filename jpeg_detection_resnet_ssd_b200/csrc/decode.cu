@@ -128,6 +128,7 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
 
     // ssd_output_decoder.py:207-209, 32 classes per pass
     bool any = false;
+    bool box_done = false;
     for (int c0 = 0; c0 < NS; c0 += 32) {
         const int nc = min(32, NS - c0);
         unsigned mask = 0;
@@ -150,10 +151,11 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            const int tot = __shfl_sync(0xffffffffu, incl, 31);
             int base = 0;
-            if (lane == 0) base = atomicAdd(&seg_count[b], tot);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane == 31) base = atomicAdd(&seg_count[b], incl);
+            // the slot reservation is in flight (an L2 round trip): decode this anchor's box meanwhile
+            if (mask && !box_done) { boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g); box_done = true; }
+            base = __shfl_sync(0xffffffffu, base, 31);
             unsigned long long* ck = reinterpret_cast<unsigned long long*>(keys) + (size_t)b * NS * A + base + (incl - cnt);
             for (unsigned mm = mask; mm; mm &= mm - 1) {
                 const int c = __ffs(mm) - 1;
@@ -190,7 +192,7 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
                 keys[((size_t)b * NS + c0 + c) * A + base + __popc(m & lt)] = KeyT::make(row[1 + c0 + c], (uint32_t)a);
         }
     }
-    if (any) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
+    if (any && !box_done) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
 }
 
 // Fallback loader: 128-bit LDG -> STS staging of one tile per CTA (any alignment).
@@ -253,11 +255,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar`.
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
