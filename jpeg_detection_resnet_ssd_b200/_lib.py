@@ -142,6 +142,7 @@ class Context(object):
         check(lib.ssdc_init(arr, len(self.devices), C.byref(h)))
         self.lib = lib
         self.handle = h
+        self.call_lock = threading.RLock()
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -279,19 +280,38 @@ def run_decode(y_pred, mode, confidence_thresh, iou_threshold, top_k, input_coor
     p.iou_thresh = float(iou_threshold) if do_nms else 0.0
     p.img_h = float(img_height) if normalize_coords else 1.0
     p.img_w = float(img_width) if normalize_coords else 1.0
+    # Device scratch per image: the input copy, worst-case candidate lists and the decoded boxes.
+    # Very large batches are processed in sub-batches so the scratch stays inside a fixed budget
+    # (SSDC_SCRATCH_GB, default 32 of the 180 GB).
+    elem = 4 if dt == F32 else 8
+    n_seg = (W - 13) if mode in (MODE_PER_CLASS, MODE_LAYER) else 1
+    per_image = A * W * elem + n_seg * A * (8 if dt == F32 else 16) + A * 4 * elem + 4 * A
+    budget = float(os.environ.get('SSDC_SCRATCH_GB', '32')) * 2 ** 30
+    n_dev = max(1, len(ctx.devices))
+    max_images = max(n_dev, int(budget // max(per_image, 1)) * n_dev)
+    if B > max_images:
+        parts = [_decode_once(ctx, y[i:i + max_images], dt, p) for i in range(0, B, max_images)]
+        return (np.concatenate([q[0] for q in parts], axis=0), np.concatenate([q[1] for q in parts]),
+                np.concatenate([q[2] for q in parts]))
+    return _decode_once(ctx, y, dt, p)
+
+
+def _decode_once(ctx, y, dt, p):
     lib = ctx.lib
+    B, A, W = y.shape
     counts = np.zeros(B, dtype=np.int32)
     total = C.c_int64(0)
-    check(lib.ssdc_decode_submit(ctx.handle, ptr(y), dt, 0, B, A, W - 12, C.byref(p)))
-    cap = B * p.top_k if p.top_k > 0 else 0
-    rows = np.empty((max(cap, 1), 6), dtype=np.float64)
-    idx = np.empty(max(cap, 1), dtype=np.int32)
-    rc = lib.ssdc_decode_collect(ctx.handle, ptr(rows), cap, ptr(counts), ptr(idx), C.byref(total))
-    if rc == ERR_CAPACITY:
-        cap = int(total.value)
+    with ctx.call_lock:          # submit + collect form one transaction on the context
+        check(lib.ssdc_decode_submit(ctx.handle, ptr(y), dt, 0, B, A, W - 12, C.byref(p)))
+        cap = B * p.top_k if p.top_k > 0 else 0
         rows = np.empty((max(cap, 1), 6), dtype=np.float64)
         idx = np.empty(max(cap, 1), dtype=np.int32)
         rc = lib.ssdc_decode_collect(ctx.handle, ptr(rows), cap, ptr(counts), ptr(idx), C.byref(total))
-    check(rc)
+        if rc == ERR_CAPACITY:
+            cap = int(total.value)
+            rows = np.empty((max(cap, 1), 6), dtype=np.float64)
+            idx = np.empty(max(cap, 1), dtype=np.int32)
+            rc = lib.ssdc_decode_collect(ctx.handle, ptr(rows), cap, ptr(counts), ptr(idx), C.byref(total))
+        check(rc)
     n = int(total.value)
     return rows[:n], counts, idx[:n]

@@ -236,3 +236,44 @@ def test_image_sweep_equals_per_class_pipeline(layout, bias, thr, ctx):
         ra, ca = product_rows7(*a)
         rb, cb = product_rows7(*b)
         assert np.array_equal(ca, cb) and np.array_equal(ra, rb)
+
+
+def test_sub_batching_and_threads(ctx, monkeypatch):
+    """(a) a batch larger than the scratch budget is processed in sub-batches with identical results;
+    (b) the encoder (Keras generator thread in the reference) and the decoder (main thread) may be
+    called concurrently on one context (hard part 8)."""
+    import threading
+    enc = synth.make_encoder(SSDInputEncoder, 'tiny')
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 4, 9, 123, bg_bias=1.0, hot=8)
+    ref = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.05, 0.45, 10, 'centroids', True, 96, 128, 'half', ctx=ctx)
+    monkeypatch.setenv('SSDC_SCRATCH_GB', '0.00002')       # ~21 KB: forces sub-batches of a few images
+    got = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.05, 0.45, 10, 'centroids', True, 96, 128, 'half', ctx=ctx)
+    monkeypatch.delenv('SSDC_SCRATCH_GB')
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+
+    gt = synth.synth_ground_truth(96, 128, 3, 16, 321)
+    y_ref = enc(gt)
+    errors = []
+
+    def encode_loop():
+        try:
+            for _ in range(20):
+                assert np.array_equal(enc(gt), y_ref, equal_nan=True)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    def decode_loop():
+        try:
+            for _ in range(20):
+                out = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.05, 0.45, 10, 'centroids', True, 96, 128, 'half', ctx=ctx)
+                assert all(np.array_equal(a, b) for a, b in zip(ref, out))
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=encode_loop), threading.Thread(target=decode_loop), threading.Thread(target=decode_loop)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
