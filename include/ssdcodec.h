@@ -103,8 +103,9 @@ int64_t ssdc_launch_count(const ssdc_ctx* ctx);
 int ssdc_profile_enable(ssdc_ctx* ctx, int on);
 int ssdc_profile_read(ssdc_ctx* ctx, double* ms /*SSDC_K_COUNT*/, int64_t* launches /*SSDC_K_COUNT*/);
 
-/* Wall-clock-free timing of a span of work on device `dev_slot` of the context:
- * records CUDA events on that device's stream.                               */
+/* Device timing of a span of work: `ssdc_timer_start` records a CUDA event on every device's
+ * stream of the context, `ssdc_timer_stop` records the closing events, waits for them and returns
+ * the longest elapsed time over the devices.                                  */
 int ssdc_timer_start(ssdc_ctx* ctx);
 int ssdc_timer_stop(ssdc_ctx* ctx, double* elapsed_ms /* max over devices */);
 

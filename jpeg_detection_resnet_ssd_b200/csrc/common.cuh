@@ -74,12 +74,6 @@ template <typename InT> struct KeyOf;
 template <> struct KeyOf<float>  { typedef Key64  type; };
 template <> struct KeyOf<double> { typedef Key128 type; };
 
-__device__ __forceinline__ Key64 shfl_key(const Key64& k, int src) {
-    Key64 r; r.v = __shfl_sync(0xffffffffu, k.v, src); return r;
-}
-__device__ __forceinline__ Key128 shfl_key(const Key128& k, int src) {
-    Key128 r; r.hi = __shfl_sync(0xffffffffu, k.hi, src); r.lo = __shfl_sync(0xffffffffu, k.lo, src); return r;
-}
 __device__ __forceinline__ Key64 shfl_xor_key(const Key64& k, int m) {
     Key64 r; r.v = __shfl_xor_sync(0xffffffffu, k.v, m); return r;
 }

@@ -6,19 +6,21 @@
 //   _greedy_nms/_greedy_nms2 .../ssd_output_decoder.py:77-109
 //   DecodeDetections{,Fast}  /root/reference/localisation_part/keras_layers/keras_layer_DecodeDetections{,Fast}.py
 //
-// Kernels (one family per numpy stage):
-//   D1 decode_filter_kernel : stream y_pred (B, A, C+12) once from HBM through shared memory with
-//                             128-bit coalesced loads; per (image, class) confidence threshold with
-//                             warp-ballot compaction into per-segment key lists; anchor-offset decode
-//                             of every anchor that produced a candidate.
+// Kernels (one family per numpy stage; details in DESIGN.md section 3):
+//   D1 decode_filter_tma_kernel : stream y_pred (B, A, C+12) once from HBM: warp-specialised persistent
+//                             CTAs, TMA bulk copies of whole-row tiles into a shared-memory ring; per
+//                             (anchor, class) confidence threshold, warp-aggregated compaction, anchor-offset
+//                             decode of every anchor that produced a candidate (decode_filter_kernel: LDG
+//                             fallback for unaligned inputs).
+//   S  sweep_kernel         : hot configuration (finite top_k): per image radix-select + sort of the best
+//                             candidates and ONE descending class-aware NMS sweep that stops at top_k.
+//   general path (top_k='all', decode_detections_fast, float64 input, greedy_nms):
 //      plan_kernel          : bins the segments by size into device-side work lists.
-//   D2 sort_kernel          : segmented bitonic sort by (score desc, anchor asc), persistent CTAs
-//                             pulling segments from the work lists (shared memory, global for huge).
-//   D3 nms_kernel           : greedy NMS, one warp per segment: 32 candidates per step are tested
-//                             against the kept list (shared-memory cache) and resolved among
-//                             themselves with ballots; stops at the per-segment cap.
+//   D2 sort_kernel          : segmented bitonic sort by (score desc, anchor asc), persistent CTAs.
+//   D3 nms_kernel           : greedy NMS, one warp per segment, raw-corner screening + compacted exact
+//                             pair decisions + bit-mask resolution; stops at the per-segment cap.
 //   D4 count_scan_kernel +  : per image totals, exclusive scan to packed row offsets,
-//      emit_kernel            cross-class top-k (bitonic sort of composite keys) and row output.
+//      emit_merge_kernel      cross-class top-k as a warp k-way merge, row output.
 #include "common.cuh"
 #include "ctx.cuh"
 #include <math.h>
@@ -31,7 +33,6 @@ constexpr int NMS_WARPS = 4;
 constexpr int NBINS = 5;          // 0: nms list, 1..4: sort bins
 constexpr int CNT_LIST = 0;       // counters[0..4]  list sizes
 constexpr int CNT_CURSOR = 8;     // counters[8..12] work cursors
-constexpr int CNT_TOTAL = 16;
 constexpr int SORT_BYTES1 = 8 * 1024, SORT_BYTES2 = 32 * 1024, SORT_BYTES3 = 128 * 1024;   // shared-memory sort bins
 
 template <typename T> struct alignas(16) SBox { T x0, y0, x1, y1; };
@@ -390,13 +391,6 @@ __global__ void sort_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg
 // ---------------------------------------------------------------------------
 // D3: greedy NMS, one warp per segment
 // ---------------------------------------------------------------------------
-template <typename StoreT, typename IouT>
-__device__ __forceinline__ Box<IouT> load_box(const SBox<StoreT>* __restrict__ bx, uint32_t anchor,
-                                              IouT sx, IouT sy, IouT d) {
-    SBox<StoreT> s = bx[anchor];
-    return make_box<IouT>((IouT)s.x0 * sx, (IouT)s.y0 * sy, (IouT)s.x1 * sx, (IouT)s.y1 * sy, d);
-}
-
 // ---------------------------------------------------------------------------
 // Pair decisions.  The reference keeps a box iff `iou <= iou_threshold`
 // (ssd_output_decoder.py:91; NaN => dropped) with iou = RN(inter / union).
