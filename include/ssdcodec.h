@@ -233,6 +233,23 @@ int ssdc_match_bipartite_greedy(ssdc_ctx* ctx, const double* weights, int64_t m,
 int ssdc_match_multi(ssdc_ctx* ctx, const double* weights, int64_t m, int64_t n, double threshold,
                      int64_t* out_gt, int64_t* out_anchor, int64_t* n_matches);
 
+/* ---- evaluation --------------------------------------------
+ * Evaluator.match_predictions  eval_utils/average_precision_evaluator.py:570-777.
+ * Predictions of all classes back to back: class c (1..n_classes) owns
+ * [pred_class_offsets[c], pred_class_offsets[c+1]) (pred_class_offsets has n_classes+2 entries,
+ * entry 0 unused, entry 1 == 0); `pred_image` is the dense image index of each prediction, confidences
+ * and boxes are float32 like the reference's structured array.  Ground truth rows
+ * [class, xmin, ymin, xmax, ymax] of image i are [gt_image_offsets[i], gt_image_offsets[i+1]);
+ * `gt_neutral` may be NULL.  Per class the predictions are ordered by descending confidence (stable:
+ * ties keep their original order); outputs are in that order: `out_order` (index inside the class),
+ * true / false positive flags and their running sums.  `only_first != 0` reproduces the reference's
+ * `verbose=False` behaviour (only the best prediction of every class is evaluated, :692-696). */
+int ssdc_voc_match(ssdc_ctx* ctx, const int32_t* pred_image, const float* pred_conf, const float* pred_box,
+                   const int64_t* pred_class_offsets, int n_classes,
+                   const double* gt, const uint8_t* gt_neutral, const int64_t* gt_image_offsets,
+                   int64_t n_images, double iou_threshold, int border_pixels, int only_first,
+                   int32_t* out_order, int32_t* out_tp, int32_t* out_fp, int32_t* out_ctp, int32_t* out_cfp);
+
 #ifdef __cplusplus
 }
 #endif

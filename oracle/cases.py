@@ -208,3 +208,53 @@ def thin_inputs(seed=301):
     out['nms_rows'] = np.concatenate([rng.integers(1, 4, (300, 1)).astype(float),
                                       np.round(rng.uniform(0, 1, (300, 1)), 2), nb], axis=1)
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# VOC evaluation cases
+# ----------------------------------------------------------------------------------------
+VOC_CASES = [
+    dict(name='voc_basic', seed=401, n_images=60, n_classes=5, kwargs=dict(matching_iou_threshold=0.5, border_pixels='include', sorting_algorithm='mergesort')),
+    dict(name='voc_neutral', seed=402, n_images=40, n_classes=4, neutral=True, kwargs=dict(matching_iou_threshold=0.5, border_pixels='include', sorting_algorithm='mergesort')),
+    dict(name='voc_ties_half', seed=403, n_images=30, n_classes=3, quantize=20, kwargs=dict(matching_iou_threshold=0.3, border_pixels='half', sorting_algorithm='mergesort')),
+    dict(name='voc_under_area', seed=404, n_images=30, n_classes=3, ignore_under_area=900, kwargs=dict(matching_iou_threshold=0.5, border_pixels='exclude', sorting_algorithm='mergesort')),
+    dict(name='voc_quiet_quirk', seed=405, n_images=20, n_classes=3, verbose=False, kwargs=dict(matching_iou_threshold=0.5, border_pixels='include', sorting_algorithm='mergesort')),
+    dict(name='voc_large', seed=406, n_images=400, n_classes=20, dets_per_image=60, kwargs=dict(matching_iou_threshold=0.5, border_pixels='include', sorting_algorithm='mergesort')),
+]
+
+
+def build_voc_input(case):
+    """Synthetic dataset + detections: integer ground-truth boxes, detections = jittered copies of some of
+    them (several per object: duplicates), plus random false positives, random confidences."""
+    rng = np.random.default_rng(case['seed'])
+    n_images, C = case['n_images'], case['n_classes']
+    labels, neutral, image_ids = [], [], []
+    for i in range(n_images):
+        m = int(rng.integers(0 if i % 7 == 3 else 1, 9))
+        w = rng.integers(12, 200, size=m); h = rng.integers(12, 200, size=m)
+        x0 = rng.integers(0, 300 - 10, size=m); y0 = rng.integers(0, 300 - 10, size=m)
+        cls = rng.integers(1, C + 1, size=m)
+        labels.append(np.stack([cls, x0, y0, x0 + w, y0 + h], axis=1).astype(np.int64).reshape(m, 5))
+        neutral.append(rng.uniform(size=m) < 0.25)
+        image_ids.append('%06d' % (1000 + 3 * i))
+    preds = [[] for _ in range(C + 1)]
+    per_img = case.get('dets_per_image', 14)
+    for i in range(n_images):
+        lab = labels[i]
+        for _ in range(per_img):
+            if lab.shape[0] and rng.uniform() < 0.7:
+                g = lab[int(rng.integers(0, lab.shape[0]))]
+                jit = rng.normal(0, 6.0, size=4)
+                box = g[1:5] + jit
+                c = int(g[0]) if rng.uniform() < 0.85 else int(rng.integers(1, C + 1))
+            else:
+                x0, y0 = rng.uniform(0, 250, size=2)
+                box = np.array([x0, y0, x0 + rng.uniform(5, 150), y0 + rng.uniform(5, 150)])
+                c = int(rng.integers(1, C + 1))
+            conf = float(rng.uniform(0.01, 1.0))
+            if case.get('quantize'):
+                conf = round(conf * case['quantize']) / case['quantize']
+            preds[c].append((image_ids[i], conf, round(float(box[0]), 1), round(float(box[1]), 1),
+                             round(float(box[2]), 1), round(float(box[3]), 1)))
+    return dict(labels=labels, eval_neutral=neutral if case.get('neutral') else None, image_ids=image_ids,
+                prediction_results=preds, n_classes=C)

@@ -156,6 +156,51 @@ def golden_thin(ref):
     print('thin ops: %d arrays' % len(out))
 
 
+def golden_voc(evmod, case):
+    from oracle import voc_eval_oracle as vo
+    inp = cases.build_voc_input(case)
+    C = inp['n_classes']
+
+    class DG(object):
+        pass
+    dg = DG()
+    dg.labels, dg.image_ids, dg.eval_neutral = inp['labels'], inp['image_ids'], inp['eval_neutral']
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ev = evmod.Evaluator(model=None, n_classes=C, data_generator=dg, model_mode='inference',
+                             ignore_under_area=case.get('ignore_under_area', 0))
+    ev.prediction_results = inp['prediction_results']
+    verbose = case.get('verbose', True)
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        num = ev.get_num_gt_per_class(ignore_neutral_boxes=True, verbose=False, ret=True)
+        tp, fp, ctp, cfp = ev.match_predictions(ignore_neutral_boxes=True, verbose=verbose, ret=True, **case['kwargs'])
+        prec, rec = ev.compute_precision_recall(verbose=False, ret=True)
+        ap_s = ev.compute_average_precisions(mode='sample', num_recall_points=11, verbose=False, ret=True)
+        ap_i = ev.compute_average_precisions(mode='integrate', verbose=False, ret=True)
+    o_num = vo.get_num_gt_per_class(inp['labels'], inp['eval_neutral'], C, True, case.get('ignore_under_area', 0))
+    o_tp, o_fp, o_ctp, o_cfp = vo.match_predictions(inp['prediction_results'], inp['labels'], inp['image_ids'], inp['eval_neutral'], C,
+                                                    ignore_neutral_boxes=True, verbose=verbose,
+                                                    ignore_under_area=case.get('ignore_under_area', 0), **case['kwargs'])
+    assert same(np.asarray(num), np.asarray(o_num))
+    for c in range(1, C + 1):
+        assert same(np.asarray(tp[c]), np.asarray(o_tp[c])) and same(np.asarray(fp[c]), np.asarray(o_fp[c])), case['name']
+        assert same(np.asarray(ctp[c]), np.asarray(o_ctp[c])) and same(np.asarray(cfp[c]), np.asarray(o_cfp[c]))
+    o_prec, o_rec = vo.compute_precision_recall(o_ctp, o_cfp, o_num, C)
+    for c in range(1, C + 1):
+        assert same(np.asarray(prec[c]), np.asarray(o_prec[c])) and same(np.asarray(rec[c]), np.asarray(o_rec[c]))
+    assert np.array_equal(np.asarray(ap_s, dtype=float), np.asarray(vo.compute_average_precisions(o_prec, o_rec, C, 'sample', 11), dtype=float))
+    assert np.array_equal(np.asarray(ap_i, dtype=float), np.asarray(vo.compute_average_precisions(o_prec, o_rec, C, 'integrate'), dtype=float))
+    out = dict(num_gt=np.asarray(num), ap_sample=np.asarray(ap_s, dtype=float), ap_integrate=np.asarray(ap_i, dtype=float),
+               case=json.dumps(case))
+    for c in range(1, C + 1):
+        out['tp_%d' % c] = np.asarray(tp[c]); out['fp_%d' % c] = np.asarray(fp[c])
+    np.savez_compressed(os.path.join(GOLDEN, case['name'] + '.npz'), **out)
+    print('%-26s preds %d  tp %d  mAP(sample) %.4f' % (case['name'], sum(len(p) for p in inp['prediction_results']),
+                                                      sum(int(np.sum(tp[c])) for c in range(1, C + 1)), float(np.mean(ap_s[1:]))))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_loader.load()
@@ -169,6 +214,10 @@ def main():
             golden_encode(ref, case)
     if not only or 'thin' in only:
         golden_thin(ref)
+    evmod = ref_loader.load_evaluator()
+    for case in cases.VOC_CASES:
+        if not only or case['name'] in only:
+            golden_voc(evmod, case)
 
 
 if __name__ == '__main__':

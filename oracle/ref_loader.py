@@ -49,3 +49,42 @@ def load():
                 sys.modules.pop(k)
         sys.modules.update(saved)
     return ns
+
+
+def load_evaluator():
+    """The reference's eval_utils.average_precision_evaluator module.  Its imports pull in the data
+    generators, which need third-party packages that are absent here (bs4, h5py, keras, jpeg2dct ...);
+    none of them is touched by the evaluation core, so they are replaced by empty stub modules."""
+    import types
+    if not available():
+        raise RuntimeError('reference not present at ' + REF_ROOT)
+    if not hasattr(np, 'float'):
+        np.float = float
+    if not hasattr(np, 'int'):
+        np.int = int
+    stubs = ['bs4', 'h5py', 'jpeg2dct', 'jpeg2dct.numpy', 'jpegdecoder', 'keras', 'keras.preprocessing',
+             'keras.preprocessing.image', 'keras.utils', 'tensorflow']
+    added = []
+    for name in stubs:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+            added.append(name)
+    sys.modules['bs4'].BeautifulSoup = getattr(sys.modules['bs4'], 'BeautifulSoup', object)
+    sys.modules['keras.utils'].Sequence = getattr(sys.modules['keras.utils'], 'Sequence', object)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k.split('.')[0] in ('ssd_encoder_decoder', 'bounding_box_utils', 'eval_utils', 'data_generator')}
+    sys.path.insert(0, REF_ROOT)
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            mod = importlib.import_module('eval_utils.average_precision_evaluator')
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k in list(sys.modules):
+            if k.split('.')[0] in ('ssd_encoder_decoder', 'bounding_box_utils', 'eval_utils', 'data_generator'):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+        for name in added:
+            sys.modules.pop(name, None)
+    return mod

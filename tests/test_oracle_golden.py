@@ -119,3 +119,34 @@ def test_oracle_vs_live_reference_random(seed):
     r = ref.decoder.decode_detections_fast(yr, 0.5, 0.45, 'all', 'centroids', True, 96, 128)
     o = orc.decode_detections_fast(yo, 0.5, 0.45, 'all', 'centroids', True, 96, 128)
     assert all(np.array_equal(a, b) for a, b in zip(r, o))
+
+
+# ---------------------------------------------------------------------------
+# VOC evaluation core
+# ---------------------------------------------------------------------------
+from oracle import voc_eval_oracle as voc
+
+
+def run_voc_oracle(case):
+    inp = cases.build_voc_input(case)
+    C = inp['n_classes']
+    area = case.get('ignore_under_area', 0)
+    num = voc.get_num_gt_per_class(inp['labels'], inp['eval_neutral'], C, True, area)
+    tp, fp, ctp, cfp = voc.match_predictions(inp['prediction_results'], inp['labels'], inp['image_ids'], inp['eval_neutral'], C,
+                                             ignore_neutral_boxes=True, verbose=case.get('verbose', True),
+                                             ignore_under_area=area, **case['kwargs'])
+    prec, rec = voc.compute_precision_recall(ctp, cfp, num, C)
+    ap_s = voc.compute_average_precisions(prec, rec, C, 'sample', 11)
+    ap_i = voc.compute_average_precisions(prec, rec, C, 'integrate')
+    return inp, num, tp, fp, ap_s, ap_i
+
+
+@pytest.mark.parametrize('case', [c for c in cases.VOC_CASES if c['name'] != 'voc_large'], ids=lambda c: c['name'])
+def test_voc_oracle_matches_golden(case):
+    g = load_golden(case['name'])
+    inp, num, tp, fp, ap_s, ap_i = run_voc_oracle(case)
+    assert np.array_equal(num, g['num_gt'])
+    for c in range(1, inp['n_classes'] + 1):
+        assert np.array_equal(tp[c], g['tp_%d' % c]) and np.array_equal(fp[c], g['fp_%d' % c])
+    assert np.array_equal(np.asarray(ap_s, dtype=float), g['ap_sample'])
+    assert np.array_equal(np.asarray(ap_i, dtype=float), g['ap_integrate'])
