@@ -142,3 +142,27 @@ def test_drop_in_import_paths():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
     assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
+
+
+def test_drop_in_keeps_unreplaced_reference_modules(tmp_path):
+    """The reference imports modules next to the replaced ones (`keras_layers.keras_layer_AnchorBoxes`,
+    `eval_utils.coco_utils`, ...); with the replacement directory first on sys.path they must still resolve to
+    the reference's own packages, while the replaced modules resolve to this repo."""
+    import sys
+    fake = tmp_path / 'localisation_part'
+    for pkg, mod in (('keras_layers', 'keras_layer_AnchorBoxes'), ('eval_utils', 'coco_utils'),
+                     ('eval_utils', 'average_precision_evaluator'), ('keras_layers', 'keras_layer_DecodeDetections')):
+        (fake / pkg).mkdir(parents=True, exist_ok=True)
+        (fake / pkg / '__init__.py').write_text('')
+        (fake / pkg / (mod + '.py')).write_text("ORIGIN = 'reference'\n")
+    code = (
+        "from keras_layers.keras_layer_AnchorBoxes import ORIGIN as a\n"
+        "from eval_utils.coco_utils import ORIGIN as b\n"
+        "from eval_utils.average_precision_evaluator import Evaluator\n"
+        "from keras_layers.keras_layer_DecodeDetections import DecodeDetections\n"
+        "import eval_utils.average_precision_evaluator as m\n"
+        "assert a == b == 'reference' and not hasattr(m, 'ORIGIN')\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'), str(fake)]))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
+    assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
