@@ -77,6 +77,9 @@ int ssdc_init(const int* device_ids, int n_devices, ssdc_ctx** out) {
         d.sm_count = prop.multiProcessorCount;
         if (cudaSetDevice(d.device) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreate(&d.t0) != cudaSuccess || cudaEventCreate(&d.t1) != cudaSuccess) {
             set_error("ssdc_init: stream/event creation failed on device %d: %s", d.device, cudaGetErrorString(cudaGetLastError()));
             delete ctx; return SSDC_ERR_CUDA;
@@ -90,6 +93,7 @@ void ssdc_destroy(ssdc_ctx* ctx) {
     if (!ctx) return;
     for (DevCtx& d : ctx->devs) {
         cudaSetDevice(d.device);
+        if (d.stream2) cudaStreamSynchronize(d.stream2);
         if (d.stream) cudaStreamSynchronize(d.stream);
         Buf* bufs[] = {&d.y_in, &d.ints, &d.keys, &d.boxes, &d.aux_class, &d.sort_scratch, &d.merge_scratch, &d.out_rows,
                        &d.out_anchor, &d.out_count, &d.row_offset, &d.gt, &d.gt_off, &d.partial, &d.matches,
@@ -98,6 +102,9 @@ void ssdc_destroy(ssdc_ctx* ctx) {
         d.h_small.release();
         if (d.t0) cudaEventDestroy(d.t0);
         if (d.t1) cudaEventDestroy(d.t1);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     for (auto& pe : ctx->prof_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }

@@ -88,7 +88,9 @@ struct DevCtx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // side stream for work that overlaps the main stream (encoder template)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // decode scratch
     Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
     PinnedBuf h_small;

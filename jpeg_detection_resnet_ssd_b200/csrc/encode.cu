@@ -34,8 +34,14 @@ struct ssdc_encoder {
     double variances[4];
     int64_t bad_image = -1;
     // per device of the context
-    struct PerDev { ssdc::Buf anchor_box, anchor_tail, anchor_boxf; };
+    struct PerDev {
+        ssdc::Buf anchor_box, anchor_tail, anchor_boxf;
+        ssdc::Buf f_perm, f_box, f_boxf, f_grpcls, f_grpbox, f_cls;       // shape-class tables of the sparse path
+    };
     std::vector<PerDev> dev;
+    // sparse path (anchors fall into a few shape classes): see pairmatch_kernel
+    bool fast_ok = false;
+    int f_slots = 0, f_classes = 0;
 };
 
 namespace ssdc {
@@ -148,6 +154,21 @@ __global__ void anchor_prep_kernel(const double* __restrict__ anchors, int A, in
     t[0] = o[0]; t[1] = o[1]; t[2] = o[2]; t[3] = o[3];
     t[4] = c4[0]; t[5] = c4[1]; t[6] = c4[2]; t[7] = c4[3];
     t[8] = v0; t[9] = v1; t[10] = v2; t[11] = v3;
+}
+
+// slot-ordered copies of the anchor boxes for the sparse path (padding slots: NaN screening box)
+__global__ void permute_anchor_kernel(const int* __restrict__ perm, int S, const Box<double>* __restrict__ abox,
+                                      const float4* __restrict__ aboxf, Box<double>* __restrict__ pbox, float4* __restrict__ pboxf) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int a = perm[s];
+    if (a >= 0) { pbox[s] = abox[a]; pboxf[s] = aboxf[a]; }
+    else {
+        Box<double> z; z.x0 = z.y0 = z.x1 = z.y1 = z.area = 0.0;
+        pbox[s] = z;
+        float4 n; n.x = n.y = n.z = n.w = __int_as_float(0x7fc00000);
+        pboxf[s] = n;
+    }
 }
 
 __global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, GtPrep* __restrict__ out) {
@@ -452,18 +473,17 @@ match_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_of
         }
         __syncthreads();
         const int asel = s_asel;
-        // rows whose best column was just zeroed get a new best: only the chunks whose stored best
-        // is a zeroed column have to be rescanned (everything, every round, for irregular inputs)
+        // rows whose best column was just zeroed get a new best (everything, every round, for irregular inputs)
         for (int r = 0; r < m; ++r) {
             if (done[r]) continue;
             if (!irr && rb_idx[r] != asel) continue;
             const Box<double> gb = gtp[g0 + r].box;
-            for (int c = 0; c < g.chunks; ++c) {
-                const int pi = part_idx[(size_t)(g0 + r) * g.chunks + c];
-                if (irr || ((taken_bits[pi >> 5] >> (pi & 31)) & 1u))
-                    rescan_chunk(gb, abox, g.A, c, taken_bits, red_val, red_idx,
-                                 &part_val[(size_t)(g0 + r) * g.chunks + c], &part_idx[(size_t)(g0 + r) * g.chunks + c]);
-            }
+            // every chunk: E1 pruned pairs against the row's best value of that time, so the stored partial
+            // of a chunk is only guaranteed while that best stands - once it is gone, the runner-up may be a
+            // pair E1 never evaluated
+            for (int c = 0; c < g.chunks; ++c)
+                rescan_chunk(gb, abox, g.A, c, taken_bits, red_val, red_idx,
+                             &part_val[(size_t)(g0 + r) * g.chunks + c], &part_idx[(size_t)(g0 + r) * g.chunks + c]);
             if (tid == 0) {
                 double bv = -INFINITY; int bi = 0x7fffffff;
                 for (int c = 0; c < g.chunks; ++c) {
@@ -658,6 +678,49 @@ __device__ __forceinline__ void tma_store_commit_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ---- E3 template stream (overlapped path): the rows of unmatched anchors - all but a few hundred per
+// image - depend on the anchor only, not on the image.  A CTA assembles the tile of one anchor range ONCE
+// in shared memory and then issues one TMA bulk store of it per image: no per-element work at all, the
+// copy engine streams `y_encoded` out while E1 / E2 (which this kernel does not depend on) run beside it
+// on the main stream.  The matched / neutral rows are patched in afterwards (write_tma_kernel<true>).
+constexpr int ET_ROWS = 64;
+constexpr int ET_THREADS = 128;
+__global__ void __launch_bounds__(ET_THREADS)
+template_tma_kernel(const double* __restrict__ tail, EncArgs g, int tiles, int splits, int B,
+                    double* __restrict__ y, double* __restrict__ y2) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = g.W, C = g.C;
+    double* trow = reinterpret_cast<double*>(smem_raw);                 // ET_ROWS x W
+    double* trow2 = trow + (size_t)ET_ROWS * W;                          // diagnostics copy (only with y2)
+    const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
+    const int a0 = tile * ET_ROWS;
+    const int rows = min(ET_ROWS, g.A - a0);
+    const int b_lo = (int)((long long)B * split / splits), b_hi = (int)((long long)B * (split + 1) / splits);
+    const int n = rows * W;
+    for (int e = threadIdx.x; e < n; e += ET_THREADS) {
+        const int r = e / W, c = e - r * W;
+        const double v = (c < C) ? ((c == g.background_id) ? 1.0 : 0.0) : tail[(size_t)(a0 + r) * 12 + (c - C)];
+        trow[e] = v;
+        if (y2) trow2[e] = (c >= C && c < C + 4) ? 0.0 : v;             // ssd_input_encoder.py:412-416
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)((size_t)n * sizeof(double));
+        for (int b = b_lo; b < b_hi; ++b) {
+            const size_t base = ((size_t)b * g.A + a0) * W;
+            tma_store_1d(y + base, trow, bytes);
+            if (y2) tma_store_1d(y2 + base, trow2, bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+// PATCH = false: the whole tile (every row) is assembled and stored.  PATCH = true (after
+// template_tma_kernel): only rows that differ from the template - matched or neutral anchors - are
+// written, class columns and offsets only.
+template <bool PATCH>
 __global__ void __launch_bounds__(E3_THREADS)
 write_tma_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
                  const Box<double>* __restrict__ abox, const float4* __restrict__ aboxf, const double* __restrict__ tail,
@@ -666,7 +729,7 @@ write_tma_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ g
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = g.W, C = g.C;
     double* trow = reinterpret_cast<double*>(smem_raw);                                   // E3_ROWS x W
-    float4* sgf = reinterpret_cast<float4*>(trow + (size_t)E3_ROWS * W);
+    float4* sgf = reinterpret_cast<float4*>(trow + (PATCH ? (size_t)0 : (size_t)E3_ROWS * W));
     const int tile = blockIdx.x % tiles;
     const int b = blockIdx.x / tiles;
     const int a0 = tile * E3_ROWS;
@@ -707,14 +770,28 @@ write_tma_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ g
             off[0] = t[0]; off[1] = t[1]; off[2] = t[2]; off[3] = t[3];
             cls = neutral ? -1 : g.background_id;
         }
-        for (int c = 0; c < C; ++c) row[c] = 0.0;
-        if (cls >= 0) row[cls] = 1.0;
+        if (PATCH) {
+            if (gsel >= 0 || neutral) {
+                double* dst = y + ((size_t)b * g.A + a) * W;
+                for (int c = 0; c < C; ++c) dst[c] = (c == cls) ? 1.0 : 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) row[C + k] = off[k];
+                for (int k = 0; k < 4; ++k) dst[C + k] = off[k];
+                if (y2) {
+                    double* dst2 = y2 + ((size_t)b * g.A + a) * W;
+                    for (int c = 0; c < C; ++c) dst2[c] = (c == cls) ? 1.0 : 0.0;
+                }
+            }
+        } else {
+            for (int c = 0; c < C; ++c) row[c] = 0.0;
+            if (cls >= 0) row[cls] = 1.0;
 #pragma unroll
-        for (int k = 4; k < 12; ++k) row[C + k] = t[k];
+            for (int k = 0; k < 4; ++k) row[C + k] = off[k];
+#pragma unroll
+            for (int k = 4; k < 12; ++k) row[C + k] = t[k];
+        }
         if (midx) midx[(size_t)b * g.A + a] = (gsel >= 0) ? gsel : (neutral ? -2 : -1);
     }
+    if (PATCH) return;
     // generic-proxy writes to shared memory must be visible to the async proxy before the bulk store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -739,6 +816,452 @@ write_tma_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ g
             tma_store_commit_wait_read();
         }
     }
+}
+
+
+// ===========================================================================
+// Sparse path (E1 + E2 fused, then E3 patch).  Anchor sets of SSD models consist of a few SHAPE CLASSES
+// (boxes per cell x predictor layers: 30 for SSD300); all anchors of a class share width, height and
+// area up to rounding noise.  For a ground-truth row the position-independent bound
+//     iou <= min(w) * min(h) / (area_gt + area_anchor - min(w) * min(h))
+// is therefore one number per (row, class), and a whole class is skipped when that bound is below both
+// the smallest threshold that matters (pos / neg IoU limits) and the row's best IoU found so far.
+// The encoder keeps the anchors sorted by class, every class padded to whole warps, so the skip is a
+// warp-uniform branch.  One CTA per image:
+//   * slot loop: thread <-> anchor.  Per surviving (row, warp): float32 disjointness screen, exact
+//     float64 IoU for overlapping pairs; the thread keeps its anchor's np.argmax over rows (match_multi,
+//     neutral test), the warp folds its best pair into the row's running (value, first index) maximum.
+//   * the m greedy rounds of match_bipartite_greedy on the row maxima (same literal semantics as
+//     match_kernel); a row whose best column was taken is rescanned exhaustively.
+//   * `cand[b, a]`: -1 unmatched, -2 neutral, r >= 0 matched to ground-truth row r (bipartite matches are
+//     written last, in row order: last write wins, ssd_input_encoder.py:362).
+// Everything skipped is provably below the value it is compared with, so the results are those of the
+// exhaustive evaluation.
+// ===========================================================================
+constexpr int EF_MAX_M = 128;          // more ground-truth rows per image: general path
+constexpr int EF_MAX_K = 64;           // more shape classes: general path
+
+struct FastArgs {
+    const int* perm;                   // slot -> anchor index (-1: padding)
+    const Box<double>* pbox;           // slot -> anchor box (exact)
+    const float4* pboxf;               // slot -> screening box (NaN for padding)
+    const int* grp_cls;                // 32-slot group -> class
+    const float4* grp_box;             // 32-slot group -> screening box around all its anchors
+    const float4* cls;                 // class -> (w_up, h_up, area_lo, -)
+    int n_slots, K;
+};
+
+__device__ __forceinline__ float cut_of(double v) {
+    return (v > 0.0) ? __fmul_rd(__double2float_rd(v), 1.0f - 0x1p-20f) : ((v != v) ? __int_as_float(0x7fc00000) : 0.f);
+}
+
+// np.argmax-faithful warp reduction: every lane ends with the best (value, index) pair of the warp
+__device__ __forceinline__ void warp_best(double& bv, int& bi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+}
+
+// RS = ground-truth rows per lane of the warp-private row maxima: 1 (m <= 32) or 4 (m <= 128)
+template <int RS>
+__global__ void __launch_bounds__(512, 2)
+pairmatch_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
+                 int* __restrict__ cand, int* __restrict__ match) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_val[16];
+    __shared__ int red_idx[16];
+    __shared__ int s_irr, s_ntaken, s_cut2, s_round, s_more;
+    __shared__ unsigned s_rescan[4];
+    const int b = blockIdx.x;
+    const long long g0 = gt_off[b];
+    const int m = (int)(gt_off[b + 1] - g0);
+    if (m == 0) return;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int K = f.K;
+    Box<double>* sgt = reinterpret_cast<Box<double>*>(smem_raw);           // m
+    double* rb_val = reinterpret_cast<double*>(sgt + m);                   // m   row maximum ...
+    float4* sgf = reinterpret_cast<float4*>(rb_val + m);                   // m   (offset 48 m: 16-byte aligned)
+    float* ub = reinterpret_cast<float*>(sgf + m);                         // m x K  shape bounds
+    int* best_cut = reinterpret_cast<int*>(ub + (size_t)m * K);            // m   float bits: lower bound of the row maximum
+    int* rb_idx = best_cut + m;                                            // m   ... and its first index
+    int* sreg = rb_idx + m;                                                // m   row is regular
+    int* taken = sreg + m;                                                 // m   zeroed columns
+    unsigned char* done = reinterpret_cast<unsigned char*>(taken + m);     // m
+
+    const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
+    const float thr_cut = cut_of(thr_min);
+    for (int r = tid; r < m; r += T) {
+        const GtPrep* gp = gtp + g0 + r;
+        sgt[r] = gp->box; sgf[r] = gp->sf; sreg[r] = gp->regular;
+        best_cut[r] = 0; done[r] = 0;
+        match[g0 + r] = 0;                 // matches = np.zeros(num_ground_truth_boxes) (matching_utils.py:59)
+    }
+    if (tid == 0) { s_irr = 0; s_ntaken = 0; s_round = 0; s_more = 0; }
+    for (int e = tid; e < m * K; e += T) {
+        const int r = e / K, k = e - r * K;
+        const GtPrep* gp = gtp + g0 + r;
+        const float4 c = f.cls[k];
+        float u = INFINITY;
+        if (gp->regular) {
+            const float mwh = __fmul_ru(fminf(gp->w_up, c.x), fminf(gp->h_up, c.y));
+            const float den = __fsub_rd(__fadd_rd(gp->area_lo, c.z), mwh);
+            if (den > 0.f) u = __fdiv_ru(mwh, den);
+        }
+        ub[e] = u;
+    }
+    __syncthreads();
+
+    // warp-private row maxima, lane l holds rows l, l + 32, ...  Regular rows: every pair that is skipped
+    // has iou >= +0, so (0, anchor 0) is a valid start (np.argmax of an all-zero row); irregular rows
+    // are evaluated exhaustively.
+    double wv[RS];
+    int wi[RS];
+#pragma unroll
+    for (int j = 0; j < RS; ++j) {
+        const int r = 32 * j + lane;
+        const bool reg = (r < m) && sreg[r] != 0;
+        wv[j] = reg ? 0.0 : -INFINITY;
+        wi[j] = reg ? 0 : 0x7fffffff;
+    }
+
+    bool irr = false;
+    for (int base = 0; base < f.n_slots; base += T) {
+        const int slot = base + tid;
+        if (slot >= f.n_slots) break;                        // n_slots is a multiple of 32: warp-uniform
+        const int k = f.grp_cls[slot >> 5];
+        const int a = f.perm[slot];
+        const float4 af = f.pboxf[slot];
+        const float4 gbox = f.grp_box[slot >> 5];
+        const bool live = a >= 0;
+        Box<double> ab;
+        bool have_ab = false;
+        double cv = -INFINITY;
+        int cg = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < RS; ++j) {
+            if (32 * j >= m) break;
+            // rows for which this class can matter: its shape bound reaches a threshold or the row's best so far
+            const int rl = 32 * j + lane;
+            bool need = false;
+            if (rl < m) {
+                const float u = ub[rl * K + k];
+                need = !(u < thr_cut && u < __int_as_float(*reinterpret_cast<volatile int*>(&best_cut[rl])));
+                // ... and the row touches this group of anchors at all (else every iou of the group is +0)
+                if (sreg[rl] && screen_disjoint(sgf[rl], gbox)) need = false;
+            }
+            unsigned rows = __ballot_sync(0xffffffffu, need);
+            while (rows) {
+                const int rbit = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int r = 32 * j + rbit;
+                const bool rreg = sreg[r] != 0;
+                double s = 0.0;
+                if (live) {
+                    if (rreg) {
+                        if (!screen_disjoint(sgf[r], af)) {
+                            if (!have_ab) { ab = f.pbox[slot]; have_ab = true; }
+                            const Box<double> gb = sgt[r];
+                            if (!disjoint_d(gb, ab)) s = iou_boxes<double>(gb, ab);
+                        }
+                    } else {
+                        if (!have_ab) { ab = f.pbox[slot]; have_ab = true; }
+                        s = iou_boxes<double>(sgt[r], ab);
+                        irr |= (s < 0.0);
+                    }
+                    if (better(s, r, cv, cg)) { cv = s; cg = r; }
+                }
+                // row maximum: an exact zero never beats the start value of a regular row, nor does anything
+                // below the (float lower bound of the) best value any warp has found so far
+                const bool contender = live && (rreg ? (s > 0.0 && s >= (double)__int_as_float(*reinterpret_cast<volatile int*>(&best_cut[r]))) : true);
+                if (__any_sync(0xffffffffu, contender)) {
+                    double bv = contender ? s : -INFINITY;
+                    int bi = contender ? a : 0x7fffffff;
+                    warp_best(bv, bi);
+                    if (lane == rbit && better(bv, bi, wv[j], wi[j])) {
+                        wv[j] = bv; wi[j] = bi;
+                        if (rreg) atomicMax(&best_cut[r], __float_as_int(cut_of(bv)));
+                    }
+                }
+            }
+        }
+        if (live) {
+            const bool pos = g.multi && (cv >= g.pos_thr);          // matching_utils.py:109-114
+            const bool neu = cv >= g.neg_thr;                        // ssd_input_encoder.py:388-390
+            if (pos) cand[(size_t)b * g.A + a] = cg;
+            else if (neu) cand[(size_t)b * g.A + a] = -2;
+        }
+    }
+    if (__any_sync(__activemask(), irr) && lane == 0) atomicOr(&s_irr, 1);
+    // merge the warp-private maxima
+    for (int w = 0; w < nwarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < RS; ++j) {
+                const int r = 32 * j + lane;
+                if (r < m && (w == 0 || better(wv[j], wi[j], rb_val[r], rb_idx[r]))) { rb_val[r] = wv[j]; rb_idx[r] = wi[j]; }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- greedy bipartite rounds (matching_utils.py:63-77).  Warp 0 plays the rounds on its own and
+    // calls the block in only when a row lost its best column and has to be rescanned.
+    const bool irrb = s_irr != 0;
+    const int ngroups = f.n_slots >> 5;
+    while (true) {
+        if (warp == 0) {
+            int round = s_round;
+            unsigned any = 0;
+            while (round < m && !any) {
+                double bv = -INFINITY; int bg = 0x7fffffff;
+                for (int r = lane; r < m; r += 32) {
+                    const double v = rb_val[r];
+                    if (better(v, r, bv, bg)) { bv = v; bg = r; }
+                }
+                warp_best(bv, bg);
+                const int asel = rb_idx[bg];
+                __syncwarp();
+                if (lane == 0) {
+                    match[g0 + bg] = asel;
+                    rb_val[bg] = 0.0;            // weight_matrix[ground_truth_index] = 0 -> argmax 0, weight 0
+                    rb_idx[bg] = 0;
+                    done[bg] = 1;
+                    taken[round] = asel;         // weight_matrix[:, anchor_index] = 0
+                }
+                __syncwarp();
+                ++round;
+                // rows whose best column was just zeroed need a new maximum (every open row for irregular inputs)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = 32 * j + lane;
+                    const bool again = (r < m) && !done[r] && (irrb || rb_idx[r] == asel);
+                    const unsigned mk = __ballot_sync(0xffffffffu, again);
+                    if (lane == 0) s_rescan[j] = mk;
+                    any |= mk;
+                }
+            }
+            if (lane == 0) { s_round = round; s_ntaken = round; s_more = any ? 1 : 0; }
+        }
+        __syncthreads();
+        if (!s_more) break;
+        const int ntaken = s_ntaken;
+        const unsigned rescan_rows[4] = {s_rescan[0], s_rescan[1], s_rescan[2], s_rescan[3]};   // (warp 0 rewrites them next phase)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned rows = rescan_rows[j];
+            while (rows) {
+                const int r = 32 * j + __ffs(rows) - 1;
+                rows &= rows - 1;
+                // rescan of row r with the taken columns zeroed, pruned by the shape bounds against the
+                // running maximum of THIS scan (the pruning of the first pass was relative to a maximum that is gone)
+                const bool rreg = sreg[r] != 0;
+                if (tid == 0) s_cut2 = 0;
+                __syncthreads();
+                double mv = rreg ? 0.0 : -INFINITY;
+                int mi = rreg ? 0 : 0x7fffffff;
+                for (int gidx = warp; gidx < ngroups; gidx += nwarps) {
+                    const float u = ub[r * K + f.grp_cls[gidx]];
+                    if (u < __int_as_float(*reinterpret_cast<volatile int*>(&s_cut2))) continue;
+                    if (rreg && screen_disjoint(sgf[r], f.grp_box[gidx])) continue;
+                    const int slot = gidx * 32 + lane;
+                    const int a = f.perm[slot];
+                    const bool live = a >= 0;
+                    double s = 0.0;
+                    if (live) {
+                        bool tk = false;
+                        for (int t = 0; t < ntaken; ++t) tk |= (taken[t] == a);
+                        if (!tk) {
+                            if (rreg) {
+                                if (!screen_disjoint(sgf[r], f.pboxf[slot])) {
+                                    const Box<double> ab = f.pbox[slot];
+                                    const Box<double> gb = sgt[r];
+                                    if (!disjoint_d(gb, ab)) s = iou_boxes<double>(gb, ab);
+                                }
+                            } else {
+                                s = iou_boxes<double>(sgt[r], f.pbox[slot]);
+                            }
+                        }
+                    }
+                    const bool contender = live && (rreg ? (s > 0.0 && s >= (double)__int_as_float(*reinterpret_cast<volatile int*>(&s_cut2))) : true);
+                    if (__any_sync(0xffffffffu, contender)) {
+                        double bv = contender ? s : -INFINITY;
+                        int bi = contender ? a : 0x7fffffff;
+                        warp_best(bv, bi);
+                        if (better(bv, bi, mv, mi)) {
+                            mv = bv; mi = bi;
+                            if (rreg && lane == 0) atomicMax(&s_cut2, __float_as_int(cut_of(bv)));
+                        }
+                    }
+                }
+                if (lane == 0) { red_val[warp] = mv; red_idx[warp] = mi; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 1; w < nwarps; ++w)
+                        if (better(red_val[w], red_idx[w], mv, mi)) { mv = red_val[w]; mi = red_idx[w]; }
+                    rb_val[r] = mv; rb_idx[r] = mi;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    // y_encoded[i, bipartite_matches, :-8] = labels_one_hot: row order, last write wins (:362); a bipartite
+    // column is zeroed before match_multi and the neutral test, so it overrides whatever the slot loop left
+    if (tid == 0)
+        for (int r = 0; r < m; ++r) cand[(size_t)b * g.A + match[g0 + r]] = r;
+}
+
+// E3 patch of the sparse path: rows whose `cand` entry is not -1 differ from the template
+__device__ __forceinline__ void apply_one(int c, long long i, const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+                                          const double* __restrict__ tail, const EncArgs& g, double* __restrict__ y, double* __restrict__ y2) {
+    const int W = g.W, C = g.C;
+    const long long b = i / g.A;
+    const int a = (int)(i - b * g.A);
+    double* dst = y + (size_t)i * W;
+    int cls = -1;
+    if (c >= 0) {
+        const GtPrep gp = gtp[gt_off[b] + c];
+        const double* t = tail + (size_t)a * 12;
+        double an[4] = {t[4], t[5], t[6], t[7]};
+        double v[4] = {t[8], t[9], t[10], t[11]};
+        double off[4];
+        encode_offsets(gp.data, an, v, g.coords, g.log_wh, off);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[C + k] = off[k];
+        cls = gp.cls;
+    }
+    for (int k = 0; k < C; ++k) dst[k] = (k == cls) ? 1.0 : 0.0;
+    if (y2) {
+        double* dst2 = y2 + (size_t)i * W;
+        for (int k = 0; k < C; ++k) dst2[k] = (k == cls) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+apply_kernel(const int* __restrict__ cand, const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+             const double* __restrict__ tail, EncArgs g, long long total, double* __restrict__ y, double* __restrict__ y2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(cand) & 15) == 0) {
+        const long long quads = total >> 2;
+        const int4* c4 = reinterpret_cast<const int4*>(cand);
+        for (long long q = t0; q < quads; q += 2 * stride) {
+            const int4 u = c4[q];
+            int4 v = make_int4(-1, -1, -1, -1);
+            if (q + stride < quads) v = c4[q + stride];
+            if ((u.x & u.y & u.z & u.w) != -1) {
+                if (u.x != -1) apply_one(u.x, 4 * q, gtp, gt_off, tail, g, y, y2);
+                if (u.y != -1) apply_one(u.y, 4 * q + 1, gtp, gt_off, tail, g, y, y2);
+                if (u.z != -1) apply_one(u.z, 4 * q + 2, gtp, gt_off, tail, g, y, y2);
+                if (u.w != -1) apply_one(u.w, 4 * q + 3, gtp, gt_off, tail, g, y, y2);
+            }
+            if ((v.x & v.y & v.z & v.w) != -1) {
+                const long long q2 = q + stride;
+                if (v.x != -1) apply_one(v.x, 4 * q2, gtp, gt_off, tail, g, y, y2);
+                if (v.y != -1) apply_one(v.y, 4 * q2 + 1, gtp, gt_off, tail, g, y, y2);
+                if (v.z != -1) apply_one(v.z, 4 * q2 + 2, gtp, gt_off, tail, g, y, y2);
+                if (v.w != -1) apply_one(v.w, 4 * q2 + 3, gtp, gt_off, tail, g, y, y2);
+            }
+        }
+        for (long long i = 4 * quads + t0; i < total; i += stride) {
+            const int c = cand[i];
+            if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
+        }
+    } else {
+        for (long long i = t0; i < total; i += stride) {
+            const int c = cand[i];
+            if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
+        }
+    }
+}
+
+// ---- shape classes of the anchor set (host, once per encoder) ---------------------------------
+static float f_up(double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return f; }
+static float f_down(double v) { float f = (float)v; if ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
+
+struct ShapeClasses {
+    std::vector<int> perm;              // slot -> anchor (-1 padding), classes padded to multiples of 32
+    std::vector<int> grp_cls;           // group of 32 slots -> class
+    std::vector<float> grp_box;         // group -> x0, y0, x1, y1 of a box around all its anchors (rounded outward)
+    std::vector<float> cls;             // K x 4: w_up, h_up, area_lo, 0
+    int K = 0;
+};
+
+// Anchors with (nearly) the same width and height form a class; classes are ordered by descending area so
+// that the large anchors - few, and the likeliest best matches of large boxes - are visited first.
+// Returns false when the anchor set does not qualify (improper boxes, too many classes).
+static bool build_shape_classes(const std::vector<Box<double>>& ab, ShapeClasses* out) {
+    const int A = (int)ab.size();
+    std::vector<double> w(A), h(A);
+    for (int a = 0; a < A; ++a) {
+        const Box<double>& b = ab[a];
+        w[a] = b.x1 - b.x0; h[a] = b.y1 - b.y0;
+        if (!(w[a] > 0.0 && h[a] > 0.0 && b.area > 0.0 && std::isfinite(b.area) && std::isfinite(b.x0) && std::isfinite(b.y0) &&
+              std::isfinite(b.x1) && std::isfinite(b.y1))) return false;
+    }
+    const double tol = 1e-6;
+    std::vector<int> idx(A), cls_of(A, -1);
+    for (int a = 0; a < A; ++a) idx[a] = a;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return w[x] < w[y]; });
+    int K = 0;
+    for (int i0 = 0; i0 < A;) {
+        int i1 = i0 + 1;
+        while (i1 < A && w[idx[i1]] - w[idx[i1 - 1]] <= tol * w[idx[i1]]) ++i1;
+        std::vector<int> sub(idx.begin() + i0, idx.begin() + i1);
+        std::stable_sort(sub.begin(), sub.end(), [&](int x, int y) { return h[x] < h[y]; });
+        for (size_t j0 = 0; j0 < sub.size();) {
+            size_t j1 = j0 + 1;
+            while (j1 < sub.size() && h[sub[j1]] - h[sub[j1 - 1]] <= tol * h[sub[j1]]) ++j1;
+            if (K >= EF_MAX_K) return false;
+            for (size_t j = j0; j < j1; ++j) cls_of[sub[j]] = K;
+            ++K;
+            j0 = j1;
+        }
+        i0 = i1;
+    }
+    std::vector<float> wu(K, 0.f), hu(K, 0.f), al(K, INFINITY);
+    std::vector<int> count(K, 0);
+    for (int a = 0; a < A; ++a) {
+        const int k = cls_of[a];
+        wu[k] = std::max(wu[k], f_up(w[a])); hu[k] = std::max(hu[k], f_up(h[a])); al[k] = std::min(al[k], f_down(ab[a].area));
+        ++count[k];
+    }
+    std::vector<int> order(K);
+    for (int k = 0; k < K; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return al[x] > al[y]; });
+    std::vector<int> rank(K);
+    for (int i = 0; i < K; ++i) rank[order[i]] = i;
+    std::vector<int> start(K + 1, 0);
+    for (int i = 0; i < K; ++i) start[i + 1] = start[i] + ((count[order[i]] + 31) & ~31);
+    out->K = K;
+    out->perm.assign(start[K], -1);
+    out->grp_cls.assign(start[K] / 32, 0);
+    out->cls.assign((size_t)K * 4, 0.f);
+    std::vector<int> fill(K, 0);
+    for (int a = 0; a < A; ++a) {                       // ascending anchor index inside a class
+        const int i = rank[cls_of[a]];
+        out->perm[start[i] + fill[i]++] = a;
+    }
+    const int G = start[K] / 32;
+    out->grp_box.assign((size_t)G * 4, 0.f);
+    for (int gidx = 0; gidx < G; ++gidx) {
+        float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+        for (int l = 0; l < 32; ++l) {
+            const int a = out->perm[gidx * 32 + l];
+            if (a < 0) continue;
+            x0 = std::min(x0, f_down(ab[a].x0)); y0 = std::min(y0, f_down(ab[a].y0));
+            x1 = std::max(x1, f_up(ab[a].x1)); y1 = std::max(y1, f_up(ab[a].y1));
+        }
+        out->grp_box[4 * gidx] = x0; out->grp_box[4 * gidx + 1] = y0; out->grp_box[4 * gidx + 2] = x1; out->grp_box[4 * gidx + 3] = y1;
+    }
+    for (int i = 0; i < K; ++i) {
+        for (int gidx = start[i] / 32; gidx < start[i + 1] / 32; ++gidx) out->grp_cls[gidx] = i;
+        out->cls[4 * i] = wu[order[i]]; out->cls[4 * i + 1] = hu[order[i]]; out->cls[4 * i + 2] = al[order[i]];
+    }
+    return true;
 }
 
 static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, int64_t* n_gt) {
@@ -773,16 +1296,91 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     g.d = (p.border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p.border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
     g.img_h = p.img_h; g.img_w = p.img_w; g.normalize = p.normalize;
 
+    cudaStream_t st = d->stream;
+    const size_t row_bytes = (size_t)g.W * sizeof(double);
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
+                        (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)ET_ROWS * row_bytes) % 16 == 0) &&
+                        ((((size_t)enc->A % ET_ROWS) * row_bytes) % 16 == 0);
+    const bool no_overlap = getenv("SSDC_ENC_NO_OVERLAP") != nullptr;      // (diagnostic switches, read per call)
+    const size_t smem_tpl = (size_t)ET_ROWS * row_bytes * (y2_dev ? 2 : 1);
+    const bool overlap = tma_ok && !no_overlap && smem_tpl <= 64 * 1024;
+    if (overlap) {
+        // E3 template stream: independent of the ground truth, so it starts first and runs beside E1 / E2.
+        // (With per-launch profiling on, everything stays on the main stream so that each kernel is timed alone.)
+        cudaStream_t ts = ctx->profile ? st : d->stream2;
+        if (ts != st) {
+            SSDC_CUDA(cudaEventRecord(d->ev_fork, st));
+            SSDC_CUDA(cudaStreamWaitEvent(ts, d->ev_fork, 0));
+        }
+        const int tiles = (int)((enc->A + ET_ROWS - 1) / ET_ROWS);
+        int splits = (2 * d->sm_count + tiles - 1) / tiles;
+        if (splits > B) splits = (int)B;
+        if (splits < 1) splits = 1;
+        {
+            LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+            SSDC_CUDA(cudaFuncSetAttribute(template_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tpl));
+            template_tma_kernel<<<(unsigned)(tiles * splits), ET_THREADS, smem_tpl, ts>>>(enc->dev[slot].anchor_tail.as<double>(), g, tiles, splits, (int)B, y_dev, y2_dev);
+            SSDC_TRY(check_launch("template_tma_kernel"));
+        }
+        if (ts != st) SSDC_CUDA(cudaEventRecord(d->ev_join, ts));
+    }
     int64_t n_gt = 0;
     SSDC_TRY(upload_gt(d, gt, gt_offsets, b0, B, &n_gt));
-    cudaStream_t st = d->stream;
     const long long* gt_off = d->gt_off.as<long long>();
     const Box<double>* abox = enc->dev[slot].anchor_box.as<Box<double>>();
     const double* tail = enc->dev[slot].anchor_tail.as<double>();
     GtPrep* gtp = nullptr;
     int* match = nullptr;
+    if (n_gt > 0) gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (((size_t)n_gt * 5 * sizeof(double) + 63) & ~(size_t)63));
+
+    // ---- sparse path: shape classes + fused matching, then a patch of the few rows that differ from the template
+    const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
+    const bool sparse = overlap && enc->fast_ok && max_m <= EF_MAX_M && thr_min > 0.0 && thr_min < INFINITY &&
+                        (!g.multi || g.pos_thr == g.pos_thr) && g.neg_thr == g.neg_thr && getenv("SSDC_ENC_GENERAL") == nullptr;
+    if (sparse) {
+        const long long total = (long long)B * enc->A;
+        int* cand = midx_dev;
+        if (!cand) { SSDC_TRY(d->matches.ensure((size_t)total * sizeof(int))); cand = d->matches.as<int>(); }
+        if (n_gt > 0 || midx_dev) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
+        if (n_gt > 0) {
+            SSDC_TRY(d->partial.ensure((size_t)n_gt * sizeof(int)));
+            match = d->partial.as<int>();
+            {
+                LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
+                gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
+                SSDC_TRY(check_launch("gt_prep_kernel"));
+            }
+            {
+                LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
+                const ssdc_encoder::PerDev& pd = enc->dev[slot];
+                FastArgs f;
+                f.perm = pd.f_perm.as<int>(); f.pbox = pd.f_box.as<Box<double>>(); f.pboxf = pd.f_boxf.as<float4>();
+                f.grp_cls = pd.f_grpcls.as<int>(); f.grp_box = pd.f_grpbox.as<float4>(); f.cls = pd.f_cls.as<float4>(); f.n_slots = enc->f_slots; f.K = enc->f_classes;
+                const size_t mm = (size_t)max_m;
+                const size_t smem = mm * (sizeof(Box<double>) + sizeof(double) + sizeof(float4)) + mm * f.K * sizeof(float) +
+                                    mm * (4 * sizeof(int) + 1) + 32;
+                const int T = (B >= 2 * d->sm_count) ? 256 : 512;
+                if (max_m <= 32) {
+                    SSDC_CUDA(cudaFuncSetAttribute(pairmatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pairmatch_kernel<1><<<(unsigned)B, T, smem, st>>>(gtp, gt_off, f, g, cand, match);
+                } else {
+                    SSDC_CUDA(cudaFuncSetAttribute(pairmatch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pairmatch_kernel<4><<<(unsigned)B, T, smem, st>>>(gtp, gt_off, f, g, cand, match);
+                }
+                SSDC_TRY(check_launch("pairmatch_kernel"));
+            }
+        }
+        if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+        if (n_gt > 0) {
+            LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+            long long blocks = (total / 8 + 255) / 256 + 1;
+            if (blocks > (long long)d->sm_count * 16) blocks = (long long)d->sm_count * 16;
+            apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, gtp, gt_off, tail, g, total, y_dev, y2_dev);
+            SSDC_TRY(check_launch("apply_kernel"));
+        }
+        return SSDC_OK;
+    }
     if (n_gt > 0) {
-        gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (((size_t)n_gt * 5 * sizeof(double) + 63) & ~(size_t)63));
         // scratch: partials (val, idx), row bests, taken columns, done flags, matches, irregular flags
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -827,15 +1425,25 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     }
     {
         const int tiles = (int)((enc->A + E3_ROWS - 1) / E3_ROWS);
-        const size_t row_bytes = (size_t)g.W * sizeof(double);
-        const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
-                            (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)E3_ROWS * row_bytes) % 16 == 0) &&
-                            ((((size_t)enc->A % E3_ROWS) * row_bytes) % 16 == 0);
-        const size_t smem_tma = (size_t)E3_ROWS * row_bytes + (size_t)max_m * (sizeof(Box<double>) + sizeof(float4) + sizeof(int)) + 16;
+        const size_t smem_gt = (size_t)max_m * (sizeof(Box<double>) + sizeof(float4) + sizeof(int)) + 16;
+        if (overlap) {
+            // patch the rows of matched / neutral anchors once the template has landed
+            if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+            if (n_gt == 0 && !midx_dev) return SSDC_OK;
+            LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+            SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gt));
+            write_tma_kernel<true><<<(unsigned)(B * tiles), E3_THREADS, smem_gt, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
+            SSDC_TRY(check_launch("write_tma_kernel<patch>"));
+            return SSDC_OK;
+        }
+        const bool tma_ok3 = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
+                             (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)E3_ROWS * row_bytes) % 16 == 0) &&
+                             ((((size_t)enc->A % E3_ROWS) * row_bytes) % 16 == 0);
+        const size_t smem_tma = (size_t)E3_ROWS * row_bytes + smem_gt;
         LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
-        if (tma_ok && smem_tma <= 200 * 1024) {
-            SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-            write_tma_kernel<<<(unsigned)(B * tiles), E3_THREADS, smem_tma, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
+        if (tma_ok3 && smem_tma <= 200 * 1024) {
+            SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+            write_tma_kernel<false><<<(unsigned)(B * tiles), E3_THREADS, smem_tma, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
             SSDC_TRY(check_launch("write_tma_kernel"));
             return SSDC_OK;
         }
@@ -867,6 +1475,7 @@ int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const d
     for (int i = 0; i < 4; ++i) enc->variances[i] = variances[i];
     enc->dev.resize(ctx->devs.size());
     const double dd = (p->border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p->border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
+    ShapeClasses sc;
     for (size_t i = 0; i < ctx->devs.size(); ++i) {
         DevCtx& d = ctx->devs[i];
         int r = SSDC_OK;
@@ -884,8 +1493,40 @@ int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const d
             r = check_launch("anchor_prep_kernel");
         }
         if (r == SSDC_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) { set_error("anchor_prep failed: %s", cudaGetErrorString(cudaGetLastError())); r = SSDC_ERR_CUDA; }
+        if (r == SSDC_OK && i == 0) {
+            // shape classes for the sparse path, from the boxes exactly as the kernels see them
+            std::vector<Box<double>> hb((size_t)A);
+            if (cudaMemcpy(hb.data(), enc->dev[0].anchor_box.p, (size_t)A * sizeof(Box<double>), cudaMemcpyDeviceToHost) != cudaSuccess) r = SSDC_ERR_CUDA;
+            else enc->fast_ok = build_shape_classes(hb, &sc);
+            if (enc->fast_ok) { enc->f_slots = (int)sc.perm.size(); enc->f_classes = sc.K; }
+        }
+        if (r == SSDC_OK && enc->fast_ok) {
+            const size_t S = sc.perm.size();
+            ssdc_encoder::PerDev& pd = enc->dev[i];
+            if (r == SSDC_OK) r = pd.f_perm.ensure(S * sizeof(int));
+            if (r == SSDC_OK) r = pd.f_box.ensure(S * sizeof(Box<double>));
+            if (r == SSDC_OK) r = pd.f_boxf.ensure(S * sizeof(float4));
+            if (r == SSDC_OK) r = pd.f_grpcls.ensure(sc.grp_cls.size() * sizeof(int));
+            if (r == SSDC_OK) r = pd.f_grpbox.ensure(sc.grp_box.size() * sizeof(float));
+            if (r == SSDC_OK) r = pd.f_cls.ensure(sc.cls.size() * sizeof(float));
+            if (r == SSDC_OK &&
+                (cudaMemcpy(pd.f_perm.p, sc.perm.data(), S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                 cudaMemcpy(pd.f_grpcls.p, sc.grp_cls.data(), sc.grp_cls.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                 cudaMemcpy(pd.f_grpbox.p, sc.grp_box.data(), sc.grp_box.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                 cudaMemcpy(pd.f_cls.p, sc.cls.data(), sc.cls.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)) r = SSDC_ERR_CUDA;
+            if (r == SSDC_OK) {
+                LaunchScope ls(ctx, &d, SSDC_K_THIN);
+                permute_anchor_kernel<<<(unsigned)((S + 127) / 128), 128, 0, d.stream>>>(
+                    pd.f_perm.as<int>(), (int)S, pd.anchor_box.as<Box<double>>(), pd.anchor_boxf.as<float4>(), pd.f_box.as<Box<double>>(), pd.f_boxf.as<float4>());
+                r = check_launch("permute_anchor_kernel");
+                if (r == SSDC_OK && cudaStreamSynchronize(d.stream) != cudaSuccess) r = SSDC_ERR_CUDA;
+            }
+        }
         if (r != SSDC_OK) {
-            for (auto& pd : enc->dev) { pd.anchor_box.release(); pd.anchor_tail.release(); pd.anchor_boxf.release(); }
+            for (auto& pd : enc->dev) {
+                pd.anchor_box.release(); pd.anchor_tail.release(); pd.anchor_boxf.release();
+                pd.f_perm.release(); pd.f_box.release(); pd.f_boxf.release(); pd.f_grpcls.release(); pd.f_grpbox.release(); pd.f_cls.release();
+            }
             delete enc;
             return r;
         }
@@ -902,6 +1543,8 @@ void ssdc_encoder_destroy(ssdc_encoder* enc) {
         enc->dev[i].anchor_box.release();
         enc->dev[i].anchor_tail.release();
         enc->dev[i].anchor_boxf.release();
+        enc->dev[i].f_perm.release(); enc->dev[i].f_box.release(); enc->dev[i].f_boxf.release();
+        enc->dev[i].f_grpcls.release(); enc->dev[i].f_grpbox.release(); enc->dev[i].f_cls.release();
     }
     delete enc;
 }

@@ -15,6 +15,17 @@ pytestmark = pytest.mark.gpu
 OFFSET_RTOL = 1e-5    # north_star: encoded offsets within 1e-5 relative
 
 
+@pytest.fixture(autouse=True, params=['sparse', 'general', 'serial'])
+def enc_path(request, monkeypatch):
+    """Every test runs through the three encoder pipelines: shape-class sparse path (default), the general
+    kernels beside the template stream, and the fully serial general kernels."""
+    if request.param != 'sparse':
+        monkeypatch.setenv('SSDC_ENC_GENERAL', '1')
+    if request.param == 'serial':
+        monkeypatch.setenv('SSDC_ENC_NO_OVERLAP', '1')
+    return request.param
+
+
 def make(case):
     kw = synth.layout_kwargs(case['layout'], **case.get('overrides', {}))
     mod = enc_mod if case.get('log_wh', True) else enc_nolog
@@ -106,3 +117,43 @@ def test_encode_many_boxes_and_large_batch(ctx):
     yo, mo = oenc(gt[:4], return_matches=True)
     assert np.array_equal(mi[:4], mo)
     assert rel_err(y[:4], yo).max() <= OFFSET_RTOL
+
+
+def test_encode_runner_up_in_other_class(ctx):
+    """Two identical ground-truth boxes: the second one loses its best anchor in the bipartite rounds and
+    must fall back to the true runner-up - which lies in another shape class / anchor chunk than the best
+    (50 px box: best is a 42 px anchor of the first predictor layer, runner-up the 60 px anchor of the
+    second layer that contains it).  Both pipelines prune pairs against the row's best IoU, so this checks
+    that nothing pruned is needed later."""
+    kw = synth.layout_kwargs('ssd300')
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    gt = []
+    rng = np.random.default_rng(5)
+    for i in range(24):
+        cx, cy = 4 + 8 * int(rng.integers(4, 30)), 4 + 8 * int(rng.integers(4, 30))
+        half = 25 + int(rng.integers(-3, 4))
+        box = [float(rng.integers(1, 21)), cx - half, cy - half, cx + half, cy + half]
+        rows = [box, box]
+        if i % 3 == 0:
+            rows.append([3.0, cx - half, cy - half, cx + half, cy + half])          # a third claimant, other class
+        if i % 4 == 1:
+            rows.insert(0, [7.0, 20, 30, 260, 280])
+        gt.append(np.array(rows, dtype=float))
+    y, mi = enc(gt, return_matches=True)
+    yo, mo = oenc(gt, return_matches=True)
+    assert np.array_equal(mi, mo)
+    assert np.array_equal(y[:, :, :21], yo[:, :, :21])
+    assert rel_err(y, yo).max() <= OFFSET_RTOL
+
+
+def test_encode_more_rows_than_sparse_path_takes(ctx):
+    """> 128 ground-truth rows in an image (beyond the sparse path's shared-memory tables)."""
+    kw = synth.layout_kwargs('tiny')
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    gt = synth.synth_ground_truth(kw['img_height'], kw['img_width'], kw['n_classes'], 3, 17, max_boxes=170, min_boxes=140)
+    y, mi = enc(gt, return_matches=True)
+    yo, mo = oenc(gt, return_matches=True)
+    assert np.array_equal(mi, mo)
+    assert rel_err(y, yo).max() <= OFFSET_RTOL
