@@ -36,7 +36,7 @@ struct ssdc_encoder {
     // per device of the context
     struct PerDev {
         ssdc::Buf anchor_box, anchor_tail, anchor_boxf;
-        ssdc::Buf f_perm, f_box, f_boxf, f_grpcls, f_grpbox, f_cls;       // shape-class tables of the sparse path
+        ssdc::Buf f_perm, f_box, f_boxf, f_grpcls, f_grpbox, f_cls, f_clsgoff;       // shape-class tables of the sparse path
     };
     std::vector<PerDev> dev;
     // sparse path (anchors fall into a few shape classes): see pairmatch_kernel
@@ -848,6 +848,7 @@ struct FastArgs {
     const int* grp_cls;                // 32-slot group -> class
     const float4* grp_box;             // 32-slot group -> screening box around all its anchors
     const float4* cls;                 // class -> (w_up, h_up, area_lo, -)
+    const int* cls_goff;               // class -> first group (K + 1 entries)
     int n_slots, K;
 };
 
@@ -865,124 +866,190 @@ __device__ __forceinline__ void warp_best(double& bv, int& bi) {
     }
 }
 
-// RS = ground-truth rows per lane of the warp-private row maxima: 1 (m <= 32) or 4 (m <= 128)
-template <int RS>
-__global__ void __launch_bounds__(512, 2)
-pairmatch_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
-                 int* __restrict__ cand, int* __restrict__ match) {
+// shape bound of (ground-truth row, class): iou <= u for every anchor of the class (+inf: no statement)
+__device__ __forceinline__ float shape_bound(const GtPrep* gp, const float4 c) {
+    if (!gp->regular) return INFINITY;
+    const float mwh = __fmul_ru(fminf(gp->w_up, c.x), fminf(gp->h_up, c.y));
+    const float den = __fsub_rd(__fadd_rd(gp->area_lo, c.z), mwh);
+    return (den > 0.f) ? __fdiv_ru(mwh, den) : INFINITY;
+}
+
+// IoU of regular row r with the anchor in `slot`; pairs that are provably below `cut` (> 0: smaller than a
+// threshold and than the row's known best) may come back as +0, which is below everything they are compared with
+__device__ __forceinline__ double pair_iou(const Box<double>& gb, const float4& gf, float garea_lo, const float4& af, float aarea_lo,
+                                           float cut, const Box<double>* __restrict__ pbox, int slot, Box<double>& ab, bool& have_ab) {
+    if (screen_disjoint(gf, af)) return 0.0;                          // disjoint: +0 exactly
+    if (cut > 0.f) {
+        // float upper bound of the intersection over a lower bound of the union (screening boxes are rounded outward)
+        const float iw = __fsub_ru(fminf(gf.z, af.z), fmaxf(gf.x, af.x));
+        const float ih = __fsub_ru(fminf(gf.w, af.w), fmaxf(gf.y, af.y));
+        const float in_up = __fmul_ru(iw, ih);
+        const float den = __fsub_rd(__fadd_rd(garea_lo, aarea_lo), in_up);
+        if (den > 0.f && in_up < __fmul_rd(cut, den)) return 0.0;
+    }
+    if (!have_ab) { ab = pbox[slot]; have_ab = true; }
+    if (disjoint_d(gb, ab)) return 0.0;
+    return iou_boxes<double>(gb, ab);
+}
+
+// ---- Row candidate lists.  For every ground-truth row the sparse path keeps the list of ALL anchors whose
+// IoU with the row reaches a row-specific level tau_r > 0.  Whatever bipartite round asks "best anchor of row r
+// among the columns not taken yet": if a listed anchor is still free, the best free listed one is the exact
+// answer (every unlisted anchor is below tau_r, every taken column is zero), including np.argmax's
+// first-index rule, because all anchors that tie at that value are listed too.  Only a row whose list
+// ran dry (or overflowed, or has no level) is rescanned.
+constexpr int EL_CAP = 128;                   // list entries per row
+constexpr float EL_FRAC = 0.7f;               // tau_r = EL_FRAC * (best IoU inside the row's most promising class)
+
+// Seed: one warp per ground-truth row evaluates the class with the largest shape bound (where the row's
+// best anchor usually lives) exactly and derives tau_r from the best IoU found there.  Any tau_r > 0 is
+// valid; this choice keeps the lists short (a few dozen entries) and almost never dry.
+__global__ void __launch_bounds__(256)
+seed_kernel(const GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restrict__ gtau) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_gt) return;
+    const GtPrep* gp = gtp + row;
+    if (!gp->regular) { if (lane == 0) gtau[row] = 0.f; return; }
+    const int K = f.K;
+    const float u0 = (lane < K) ? shape_bound(gp, f.cls[lane]) : -1.f;
+    const float u1 = (lane + 32 < K) ? shape_bound(gp, f.cls[lane + 32]) : -1.f;
+    float bu = fmaxf(u0, u1);
+    int bk = (u0 >= u1) ? lane : lane + 32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ou = __shfl_xor_sync(0xffffffffu, bu, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ou > bu || (ou == bu && ok < bk)) { bu = ou; bk = ok; }
+    }
+    const Box<double> gb = gp->box;
+    const float4 gf = gp->sf;
+    const float garea = gp->area_lo, carea = f.cls[bk].z;
+    const int ge = f.cls_goff[bk + 1];
+    float cut = 0.f;
+    for (int gb0 = f.cls_goff[bk]; gb0 < ge; gb0 += 32) {
+        const int gl = gb0 + lane;
+        const bool want = (gl < ge) && !screen_disjoint(gf, f.grp_box[gl]);
+        unsigned gm = __ballot_sync(0xffffffffu, want);
+        while (gm) {
+            const int gidx = gb0 + __ffs(gm) - 1;
+            gm &= gm - 1;
+            const int slot = gidx * 32 + lane;
+            const int a = f.perm[slot];
+            const float4 af = f.pboxf[slot];
+            Box<double> ab = f.pbox[slot];
+            bool have_ab = true;
+            double sv = 0.0;
+            if (a >= 0) sv = pair_iou(gb, gf, garea, af, carea, cut, f.pbox, slot, ab, have_ab);
+            const int c = __reduce_max_sync(0xffffffffu, __float_as_int(cut_of(sv)));      // (non-negative floats order like ints)
+            cut = fmaxf(cut, __int_as_float(c));
+        }
+    }
+    if (lane == 0) gtau[row] = __fmul_rd(cut, EL_FRAC);
+}
+
+// E1 of the sparse path.  Grid (nblk, B): CTA (j, b) visits the 32-slot groups j, j + nblk, ... of image b,
+// one group per warp and step, thread <-> anchor.  A (row, group) pair is worked on only if the class's
+// shape bound reaches min(smallest IoU threshold, tau_r) and the group's bounding box meets the row; then
+// the float32 disjointness screen and IoU bound, and the exact float64 IoU for what is left.  The thread
+// keeps its anchor's np.argmax over the rows (match_multi + neutral test -> `cand`), pairs at or above tau_r
+// are appended to the row's candidate list.  No block-level synchronisation after the prologue.
+constexpr int EP_THREADS = 256;
+__global__ void __launch_bounds__(EP_THREADS, 4)
+pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
+            const float* __restrict__ gtau, int* __restrict__ cand, int* __restrict__ lcnt,
+            double* __restrict__ lval, int* __restrict__ lidx, int* __restrict__ img_irr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red_val[16];
-    __shared__ int red_idx[16];
-    __shared__ int s_irr, s_ntaken, s_cut2, s_round, s_more;
-    __shared__ unsigned s_rescan[4];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y, nblk = gridDim.x, blk = blockIdx.x;
     const long long g0 = gt_off[b];
     const int m = (int)(gt_off[b + 1] - g0);
     if (m == 0) return;
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = EP_THREADS / 32;
     const int K = f.K;
+    const int me = (m + 1) & ~1;                                           // (keeps the float4 array 16-byte aligned)
     Box<double>* sgt = reinterpret_cast<Box<double>*>(smem_raw);           // m
-    double* rb_val = reinterpret_cast<double*>(sgt + m);                   // m   row maximum ...
-    float4* sgf = reinterpret_cast<float4*>(rb_val + m);                   // m   (offset 48 m: 16-byte aligned)
-    float* ub = reinterpret_cast<float*>(sgf + m);                         // m x K  shape bounds
-    int* best_cut = reinterpret_cast<int*>(ub + (size_t)m * K);            // m   float bits: lower bound of the row maximum
-    int* rb_idx = best_cut + m;                                            // m   ... and its first index
-    int* sreg = rb_idx + m;                                                // m   row is regular
-    int* taken = sreg + m;                                                 // m   zeroed columns
-    unsigned char* done = reinterpret_cast<unsigned char*>(taken + m);     // m
-
+    float4* sgf = reinterpret_cast<float4*>(sgt + me);                     // m
+    float* ub = reinterpret_cast<float*>(sgf + me);                        // m x K  shape bounds
+    float* sga = ub + (size_t)me * K;                                      // m   lower bound of the area term
+    float* stau = sga + me;                                                // m   list level (0: the row keeps no list)
+    float* scut = stau + me;                                               // m   below this bound a pair cannot matter
+    int* sreg = reinterpret_cast<int*>(scut + me);                         // m   row is regular
+    float* scarea = reinterpret_cast<float*>(sreg + me);                   // K   lower bound of the class's area term
     const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
     const float thr_cut = cut_of(thr_min);
-    for (int r = tid; r < m; r += T) {
+    for (int r = tid; r < m; r += EP_THREADS) {
         const GtPrep* gp = gtp + g0 + r;
-        sgt[r] = gp->box; sgf[r] = gp->sf; sreg[r] = gp->regular;
-        best_cut[r] = 0; done[r] = 0;
-        match[g0 + r] = 0;                 // matches = np.zeros(num_ground_truth_boxes) (matching_utils.py:59)
+        sgt[r] = gp->box; sgf[r] = gp->sf; sga[r] = gp->area_lo; sreg[r] = gp->regular;
+        const float tau = gtau[g0 + r];
+        stau[r] = tau;
+        scut[r] = (tau > 0.f) ? fminf(thr_cut, __fmul_rd(tau, 1.0f - 0x1p-20f)) : thr_cut;
     }
-    if (tid == 0) { s_irr = 0; s_ntaken = 0; s_round = 0; s_more = 0; }
-    for (int e = tid; e < m * K; e += T) {
+    for (int e = tid; e < m * K; e += EP_THREADS) {
         const int r = e / K, k = e - r * K;
-        const GtPrep* gp = gtp + g0 + r;
-        const float4 c = f.cls[k];
-        float u = INFINITY;
-        if (gp->regular) {
-            const float mwh = __fmul_ru(fminf(gp->w_up, c.x), fminf(gp->h_up, c.y));
-            const float den = __fsub_rd(__fadd_rd(gp->area_lo, c.z), mwh);
-            if (den > 0.f) u = __fdiv_ru(mwh, den);
-        }
-        ub[e] = u;
+        ub[e] = shape_bound(gtp + g0 + r, f.cls[k]);
     }
+    for (int k = tid; k < K; k += EP_THREADS) scarea[k] = f.cls[k].z;
     __syncthreads();
 
-    // warp-private row maxima, lane l holds rows l, l + 32, ...  Regular rows: every pair that is skipped
-    // has iou >= +0, so (0, anchor 0) is a valid start (np.argmax of an all-zero row); irregular rows
-    // are evaluated exhaustively.
-    double wv[RS];
-    int wi[RS];
-#pragma unroll
-    for (int j = 0; j < RS; ++j) {
-        const int r = 32 * j + lane;
-        const bool reg = (r < m) && sreg[r] != 0;
-        wv[j] = reg ? 0.0 : -INFINITY;
-        wi[j] = reg ? 0 : 0x7fffffff;
-    }
-
     bool irr = false;
-    for (int base = 0; base < f.n_slots; base += T) {
-        const int slot = base + tid;
-        if (slot >= f.n_slots) break;                        // n_slots is a multiple of 32: warp-uniform
-        const int k = f.grp_cls[slot >> 5];
-        const int a = f.perm[slot];
-        const float4 af = f.pboxf[slot];
-        const float4 gbox = f.grp_box[slot >> 5];
+    const int ngroups = f.n_slots >> 5;
+    // (the loads of the next group are issued before the current one is worked on)
+    const int gstep = NW * nblk;
+    int gidx = warp * nblk + blk;
+    int k_n = 0, a_n = -1;
+    float4 gbox_n = make_float4(0.f, 0.f, 0.f, 0.f), af_n = gbox_n;
+    if (gidx < ngroups) { k_n = f.grp_cls[gidx]; gbox_n = f.grp_box[gidx]; a_n = f.perm[gidx * 32 + lane]; af_n = f.pboxf[gidx * 32 + lane]; }
+    for (; gidx < ngroups; gidx += gstep) {
+        const int slot = gidx * 32 + lane;
+        const int k = k_n;
+        const float4 gbox = gbox_n;
+        const int a = a_n;
+        const float4 af = af_n;
+        {
+            const int gn = gidx + gstep;
+            if (gn < ngroups) { k_n = f.grp_cls[gn]; gbox_n = f.grp_box[gn]; a_n = f.perm[gn * 32 + lane]; af_n = f.pboxf[gn * 32 + lane]; }
+        }
+        const float aarea = scarea[k];
         const bool live = a >= 0;
         Box<double> ab;
         bool have_ab = false;
         double cv = -INFINITY;
         int cg = 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < RS; ++j) {
-            if (32 * j >= m) break;
-            // rows for which this class can matter: its shape bound reaches a threshold or the row's best so far
-            const int rl = 32 * j + lane;
+        for (int r0 = 0; r0 < m; r0 += 32) {
+            const int rl = r0 + lane;
             bool need = false;
             if (rl < m) {
-                const float u = ub[rl * K + k];
-                need = !(u < thr_cut && u < __int_as_float(*reinterpret_cast<volatile int*>(&best_cut[rl])));
+                // the class can matter for the row: its shape bound reaches a threshold or the row's list level ...
+                need = !(ub[rl * K + k] < scut[rl]);
                 // ... and the row touches this group of anchors at all (else every iou of the group is +0)
                 if (sreg[rl] && screen_disjoint(sgf[rl], gbox)) need = false;
             }
             unsigned rows = __ballot_sync(0xffffffffu, need);
             while (rows) {
-                const int rbit = __ffs(rows) - 1;
+                const int r = r0 + __ffs(rows) - 1;
                 rows &= rows - 1;
-                const int r = 32 * j + rbit;
                 const bool rreg = sreg[r] != 0;
                 double s = 0.0;
                 if (live) {
-                    if (rreg) {
-                        if (!screen_disjoint(sgf[r], af)) {
-                            if (!have_ab) { ab = f.pbox[slot]; have_ab = true; }
-                            const Box<double> gb = sgt[r];
-                            if (!disjoint_d(gb, ab)) s = iou_boxes<double>(gb, ab);
-                        }
-                    } else {
+                    if (rreg) s = pair_iou(sgt[r], sgf[r], sga[r], af, aarea, scut[r], f.pbox, slot, ab, have_ab);
+                    else {
                         if (!have_ab) { ab = f.pbox[slot]; have_ab = true; }
                         s = iou_boxes<double>(sgt[r], ab);
                         irr |= (s < 0.0);
                     }
                     if (better(s, r, cv, cg)) { cv = s; cg = r; }
                 }
-                // row maximum: an exact zero never beats the start value of a regular row, nor does anything
-                // below the (float lower bound of the) best value any warp has found so far
-                const bool contender = live && (rreg ? (s > 0.0 && s >= (double)__int_as_float(*reinterpret_cast<volatile int*>(&best_cut[r]))) : true);
-                if (__any_sync(0xffffffffu, contender)) {
-                    double bv = contender ? s : -INFINITY;
-                    int bi = contender ? a : 0x7fffffff;
-                    warp_best(bv, bi);
-                    if (lane == rbit && better(bv, bi, wv[j], wi[j])) {
-                        wv[j] = bv; wi[j] = bi;
-                        if (rreg) atomicMax(&best_cut[r], __float_as_int(cut_of(bv)));
+                const float tau = stau[r];
+                const bool hit = live && tau > 0.f && s >= (double)tau;
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm) {
+                    int basep = 0;
+                    if (lane == 0) basep = atomicAdd(&lcnt[g0 + r], __popc(hm));
+                    basep = __shfl_sync(0xffffffffu, basep, 0) + __popc(hm & ((1u << lane) - 1u));
+                    if (hit && basep < EL_CAP) {
+                        lval[(size_t)(g0 + r) * EL_CAP + basep] = s;
+                        lidx[(size_t)(g0 + r) * EL_CAP + basep] = a;
                     }
                 }
             }
@@ -994,24 +1061,204 @@ pairmatch_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ g
             else if (neu) cand[(size_t)b * g.A + a] = -2;
         }
     }
-    if (__any_sync(__activemask(), irr) && lane == 0) atomicOr(&s_irr, 1);
-    // merge the warp-private maxima
-    for (int w = 0; w < nwarps; ++w) {
-        if (warp == w) {
+    if (__any_sync(0xffffffffu, irr) && lane == 0) atomicOr(&img_irr[b], 1);
+}
+
+// E2 of the sparse path: one CTA per image.  Warp 0 plays the m greedy rounds of match_bipartite_greedy
+// (matching_utils.py:63-77, same literal semantics as match_kernel).  A row that lost its best column
+// takes the best free entry of its candidate list (warp 0, on the spot); only when the list is dry are the
+// other warps called in for a rescan: they visit the class with the largest shape bound first (it usually
+// holds the new maximum), then every other group whose class bound reaches the running maximum of THIS
+// scan and whose bounding box meets the row.
+// `cand[b, a]`: the bipartite matches are written last, in row order (last write wins, ssd_input_encoder.py:362;
+// a bipartite column is zeroed before match_multi and the neutral test, so it overrides the first pass).
+constexpr int EG_WARPS = 8;
+
+// best free entry of row `row`'s list (all lanes get it); (-inf, INT_MAX) if none
+__device__ __forceinline__ void list_best(const double* __restrict__ lval, const int* __restrict__ lidx, long long row, int n,
+                                          const int* taken, int ntaken, double& bv, int& bi) {
+    const int lane = threadIdx.x & 31;
+    bv = -INFINITY; bi = 0x7fffffff;
+    for (int e = lane; e < n; e += 32) {
+        const double v = lval[(size_t)row * EL_CAP + e];
+        const int a = lidx[(size_t)row * EL_CAP + e];
+        bool tk = false;
+        for (int t = 0; t < ntaken; ++t) tk |= (taken[t] == a);
+        if (!tk && better(v, a, bv, bi)) { bv = v; bi = a; }
+    }
+    warp_best(bv, bi);
+}
+
+__global__ void __launch_bounds__(EG_WARPS * 32)
+greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
+              const float* __restrict__ gtau, const int* __restrict__ lcnt, const double* __restrict__ lval, const int* __restrict__ lidx,
+              const int* __restrict__ img_irr, int* __restrict__ cand, int* __restrict__ match) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_val[EG_WARPS];
+    __shared__ int red_idx[EG_WARPS];
+    __shared__ int s_round, s_more, s_cut2, s_ln;
+    __shared__ unsigned s_rescan[4];
+    __shared__ float s_ub[EF_MAX_K];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const long long g0 = gt_off[b];
+    const int m = (int)(gt_off[b + 1] - g0);
+    if (m == 0) return;
+    const int K = f.K;
+    const int ngroups = f.n_slots >> 5;
+    // the small tables of the encoder in shared memory (the rescans chase them with dependent loads)
+    float4* s_gbox = reinterpret_cast<float4*>(smem_raw);                  // ngroups
+    float4* s_cls = s_gbox + ngroups;                                      // K
+    double* rb_val = reinterpret_cast<double*>(s_cls + K);                 // m   row maximum ...
+    int* rb_idx = reinterpret_cast<int*>(rb_val + m);                      // m   ... and its first index
+    int* taken = rb_idx + m;                                               // m   zeroed columns
+    int* done = taken + m;                                                 // m
+    int* nlist = done + m;                                                 // m   usable list entries (0: none)
+    int* s_goff = nlist + m;                                               // K + 1
+    int* s_gcls = s_goff + K + 1;                                          // ngroups
+    int* s_list = s_gcls + ngroups;                                        // ngroups
+    for (int i = tid; i < ngroups; i += EG_WARPS * 32) { s_gbox[i] = f.grp_box[i]; s_gcls[i] = f.grp_cls[i]; }
+    for (int i = tid; i < K; i += EG_WARPS * 32) s_cls[i] = f.cls[i];
+    for (int i = tid; i <= K; i += EG_WARPS * 32) s_goff[i] = f.cls_goff[i];
+    const bool irrb = img_irr[b] != 0;
+    if (tid < 4) s_rescan[tid] = 0;
+    if (tid == 0) { s_round = 0; s_more = 0; }
+    __syncthreads();
+    // row maxima from the lists (the warps take rows in turn); rows without a usable list are rescanned
+    for (int r = warp; r < m; r += EG_WARPS) {
+        const int n = lcnt[g0 + r];
+        const bool usable = !irrb && gtau[g0 + r] > 0.f && n <= EL_CAP;
+        double bv; int bi;
+        list_best(lval, lidx, g0 + r, usable ? n : 0, taken, 0, bv, bi);
+        if (lane == 0) {
+            nlist[r] = usable ? n : 0;
+            rb_val[r] = bv; rb_idx[r] = bi; done[r] = 0;
+            match[g0 + r] = 0;             // matches = np.zeros(num_ground_truth_boxes) (matching_utils.py:59)
+            if (bi == 0x7fffffff) { atomicOr(&s_rescan[r >> 5], 1u << (r & 31)); s_more = 1; }
+        }
+    }
+    __syncthreads();
+    while (true) {
+        if (s_more) {
+            // ---- rescans, all warps
+            const int ntaken = s_round;
+            const unsigned rescan_rows[4] = {s_rescan[0], s_rescan[1], s_rescan[2], s_rescan[3]};   // (warp 0 rewrites them next phase)
 #pragma unroll
-            for (int j = 0; j < RS; ++j) {
-                const int r = 32 * j + lane;
-                if (r < m && (w == 0 || better(wv[j], wi[j], rb_val[r], rb_idx[r]))) { rb_val[r] = wv[j]; rb_idx[r] = wi[j]; }
+            for (int j = 0; j < 4; ++j) {
+                unsigned rows = rescan_rows[j];
+                while (rows) {
+                    const int r = 32 * j + __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    const GtPrep* gp = gtp + g0 + r;
+                    const bool rreg = gp->regular != 0;
+                    const Box<double> gb = gp->box;
+                    const float4 gf = gp->sf;
+                    const float garea = gp->area_lo;
+                    if (tid == 0) { s_cut2 = 0; s_ln = 0; }
+                    const float u0 = (lane < K) ? shape_bound(gp, s_cls[lane]) : -1.f;
+                    const float u1 = (lane + 32 < K) ? shape_bound(gp, s_cls[lane + 32]) : -1.f;
+                    if (warp == 0) {
+                        if (lane < K) s_ub[lane] = u0;
+                        if (lane + 32 < K) s_ub[lane + 32] = u1;
+                    }
+                    // the class with the largest shape bound first: it usually holds the new maximum
+                    float bu = fmaxf(u0, u1);
+                    int bk = (u0 >= u1) ? lane : lane + 32;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ou = __shfl_xor_sync(0xffffffffu, bu, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                        if (ou > bu || (ou == bu && ok < bk)) { bu = ou; bk = ok; }
+                    }
+                    __syncthreads();
+                    double mv = rreg ? 0.0 : -INFINITY;
+                    int mi = rreg ? 0 : 0x7fffffff;
+                    // one group: exact maximum of the non-taken anchors, folded into (mv, mi) / s_cut2
+                    auto visit = [&](int gidx, float carea) {
+                        const int slot = gidx * 32 + lane;
+                        const int a = f.perm[slot];
+                        const float4 af = f.pboxf[slot];
+                        Box<double> ab = f.pbox[slot];                          // (fetched with the others: one latency)
+                        bool have_ab = true;
+                        const bool live = a >= 0;
+                        const float cut2 = __int_as_float(*reinterpret_cast<volatile int*>(&s_cut2));
+                        double sv = 0.0;
+                        if (live) {
+                            bool tk = false;
+                            for (int t = 0; t < ntaken; ++t) tk |= (taken[t] == a);
+                            if (!tk) {
+                                if (rreg) sv = pair_iou(gb, gf, garea, af, carea, cut2, f.pbox, slot, ab, have_ab);
+                                else sv = iou_boxes<double>(gb, ab);
+                            }
+                        }
+                        const bool contender = live && (rreg ? (sv > 0.0 && sv >= (double)cut2) : true);
+                        if (__any_sync(0xffffffffu, contender)) {
+                            double cbv = contender ? sv : -INFINITY;
+                            int cbi = contender ? a : 0x7fffffff;
+                            warp_best(cbv, cbi);
+                            if (better(cbv, cbi, mv, mi)) {
+                                mv = cbv; mi = cbi;
+                                if (rreg && lane == 0) atomicMax(&s_cut2, __float_as_int(cut_of(cbv)));
+                            }
+                        }
+                    };
+                    {
+                        const int ge = s_goff[bk + 1];
+                        const float carea = s_cls[bk].z;
+                        for (int gb0 = s_goff[bk]; gb0 < ge; gb0 += 32) {
+                            const int gl = gb0 + lane;
+                            bool want = gl < ge;
+                            if (want && rreg) want = !screen_disjoint(gf, s_gbox[gl]);
+                            unsigned gm = __ballot_sync(0xffffffffu, want);
+                            int nth = 0;
+                            while (gm) {
+                                const int gidx = gb0 + __ffs(gm) - 1;
+                                gm &= gm - 1;
+                                if ((nth++ % EG_WARPS) == warp) visit(gidx, carea);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    // every other group that can still matter
+                    {
+                        const float cut2 = __int_as_float(*reinterpret_cast<volatile int*>(&s_cut2));
+                        for (int g1 = tid; g1 < ((ngroups + 31) & ~31); g1 += EG_WARPS * 32) {
+                            bool want = false;
+                            if (g1 < ngroups) {
+                                const int kk = s_gcls[g1];
+                                want = kk != bk;
+                                if (want && rreg) want = !(s_ub[kk] < cut2) && !screen_disjoint(gf, s_gbox[g1]);
+                            }
+                            const unsigned wm = __ballot_sync(0xffffffffu, want);
+                            int basep = 0;
+                            if (lane == 0 && wm) basep = atomicAdd(&s_ln, __popc(wm));
+                            basep = __shfl_sync(0xffffffffu, basep, 0);
+                            if (want) s_list[basep + __popc(wm & ((1u << lane) - 1u))] = g1;
+                        }
+                    }
+                    __syncthreads();
+                    {
+                        const int n = s_ln;
+                        for (int i = warp; i < n; i += EG_WARPS) {
+                            const int gidx = s_list[i];
+                            const int kk = s_gcls[gidx];
+                            if (rreg && s_ub[kk] < __int_as_float(*reinterpret_cast<volatile int*>(&s_cut2))) continue;
+                            visit(gidx, s_cls[kk].z);
+                        }
+                    }
+                    if (lane == 0) { red_val[warp] = mv; red_idx[warp] = mi; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int w = 1; w < EG_WARPS; ++w)
+                            if (better(red_val[w], red_idx[w], mv, mi)) { mv = red_val[w]; mi = red_idx[w]; }
+                        rb_val[r] = mv; rb_idx[r] = mi;
+                        nlist[r] = 0;                  // from now on the list says nothing about this row
+                    }
+                    __syncthreads();
+                }
             }
         }
-        __syncthreads();
-    }
-
-    // ---- greedy bipartite rounds (matching_utils.py:63-77).  Warp 0 plays the rounds on its own and
-    // calls the block in only when a row lost its best column and has to be rescanned.
-    const bool irrb = s_irr != 0;
-    const int ngroups = f.n_slots >> 5;
-    while (true) {
+        // ---- rounds, warp 0, until the block is needed again
         if (warp == 0) {
             int round = s_round;
             unsigned any = 0;
@@ -1036,83 +1283,33 @@ pairmatch_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ g
                 // rows whose best column was just zeroed need a new maximum (every open row for irregular inputs)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int r = 32 * j + lane;
-                    const bool again = (r < m) && !done[r] && (irrb || rb_idx[r] == asel);
-                    const unsigned mk = __ballot_sync(0xffffffffu, again);
-                    if (lane == 0) s_rescan[j] = mk;
-                    any |= mk;
+                    const int rr = 32 * j + lane;
+                    const bool again = (rr < m) && !done[rr] && (irrb || rb_idx[rr] == asel);
+                    unsigned mk = __ballot_sync(0xffffffffu, again);
+                    unsigned dry = 0;
+                    while (mk) {
+                        const int bit = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        const int r = 32 * j + bit;
+                        double lv; int li;
+                        list_best(lval, lidx, g0 + r, nlist[r], taken, round, lv, li);
+                        if (li == 0x7fffffff) dry |= 1u << bit;
+                        else if (lane == 0) { rb_val[r] = lv; rb_idx[r] = li; }
+                    }
+                    if (lane == 0) s_rescan[j] = dry;
+                    any |= dry;
                 }
+                __syncwarp();
             }
-            if (lane == 0) { s_round = round; s_ntaken = round; s_more = any ? 1 : 0; }
+            if (lane == 0) { s_round = round; s_more = any ? 1 : 0; }
         }
         __syncthreads();
         if (!s_more) break;
-        const int ntaken = s_ntaken;
-        const unsigned rescan_rows[4] = {s_rescan[0], s_rescan[1], s_rescan[2], s_rescan[3]};   // (warp 0 rewrites them next phase)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned rows = rescan_rows[j];
-            while (rows) {
-                const int r = 32 * j + __ffs(rows) - 1;
-                rows &= rows - 1;
-                // rescan of row r with the taken columns zeroed, pruned by the shape bounds against the
-                // running maximum of THIS scan (the pruning of the first pass was relative to a maximum that is gone)
-                const bool rreg = sreg[r] != 0;
-                if (tid == 0) s_cut2 = 0;
-                __syncthreads();
-                double mv = rreg ? 0.0 : -INFINITY;
-                int mi = rreg ? 0 : 0x7fffffff;
-                for (int gidx = warp; gidx < ngroups; gidx += nwarps) {
-                    const float u = ub[r * K + f.grp_cls[gidx]];
-                    if (u < __int_as_float(*reinterpret_cast<volatile int*>(&s_cut2))) continue;
-                    if (rreg && screen_disjoint(sgf[r], f.grp_box[gidx])) continue;
-                    const int slot = gidx * 32 + lane;
-                    const int a = f.perm[slot];
-                    const bool live = a >= 0;
-                    double s = 0.0;
-                    if (live) {
-                        bool tk = false;
-                        for (int t = 0; t < ntaken; ++t) tk |= (taken[t] == a);
-                        if (!tk) {
-                            if (rreg) {
-                                if (!screen_disjoint(sgf[r], f.pboxf[slot])) {
-                                    const Box<double> ab = f.pbox[slot];
-                                    const Box<double> gb = sgt[r];
-                                    if (!disjoint_d(gb, ab)) s = iou_boxes<double>(gb, ab);
-                                }
-                            } else {
-                                s = iou_boxes<double>(sgt[r], f.pbox[slot]);
-                            }
-                        }
-                    }
-                    const bool contender = live && (rreg ? (s > 0.0 && s >= (double)__int_as_float(*reinterpret_cast<volatile int*>(&s_cut2))) : true);
-                    if (__any_sync(0xffffffffu, contender)) {
-                        double bv = contender ? s : -INFINITY;
-                        int bi = contender ? a : 0x7fffffff;
-                        warp_best(bv, bi);
-                        if (better(bv, bi, mv, mi)) {
-                            mv = bv; mi = bi;
-                            if (rreg && lane == 0) atomicMax(&s_cut2, __float_as_int(cut_of(bv)));
-                        }
-                    }
-                }
-                if (lane == 0) { red_val[warp] = mv; red_idx[warp] = mi; }
-                __syncthreads();
-                if (tid == 0) {
-                    for (int w = 1; w < nwarps; ++w)
-                        if (better(red_val[w], red_idx[w], mv, mi)) { mv = red_val[w]; mi = red_idx[w]; }
-                    rb_val[r] = mv; rb_idx[r] = mi;
-                }
-                __syncthreads();
-            }
-        }
     }
-    __syncthreads();
-    // y_encoded[i, bipartite_matches, :-8] = labels_one_hot: row order, last write wins (:362); a bipartite
-    // column is zeroed before match_multi and the neutral test, so it overrides whatever the slot loop left
     if (tid == 0)
         for (int r = 0; r < m; ++r) cand[(size_t)b * g.A + match[g0 + r]] = r;
 }
+
 
 // E3 patch of the sparse path: rows whose `cand` entry is not -1 differ from the template
 __device__ __forceinline__ void apply_one(int c, long long i, const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
@@ -1140,41 +1337,48 @@ __device__ __forceinline__ void apply_one(int c, long long i, const GtPrep* __re
     }
 }
 
-__global__ void __launch_bounds__(256)
+// Each CTA sweeps windows of AP_WIN candidates: the few that are not -1 are queued in shared memory and
+// then worked on by consecutive threads (the rows are long serial jobs - a warp with one such lane would
+// otherwise idle 31 lanes for the whole job, one job after the other).
+constexpr int AP_THREADS = 256;
+constexpr int AP_WIN = AP_THREADS * 8;
+__global__ void __launch_bounds__(AP_THREADS)
 apply_kernel(const int* __restrict__ cand, const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
              const double* __restrict__ tail, EncArgs g, long long total, double* __restrict__ y, double* __restrict__ y2) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((reinterpret_cast<uintptr_t>(cand) & 15) == 0) {
-        const long long quads = total >> 2;
-        const int4* c4 = reinterpret_cast<const int4*>(cand);
-        for (long long q = t0; q < quads; q += 2 * stride) {
-            const int4 u = c4[q];
-            int4 v = make_int4(-1, -1, -1, -1);
-            if (q + stride < quads) v = c4[q + stride];
+    __shared__ int q_pos[AP_WIN];
+    __shared__ int q_n;
+    const int tid = threadIdx.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(cand) & 15) == 0;
+    for (long long w0 = (long long)blockIdx.x * AP_WIN; w0 < total; w0 += (long long)gridDim.x * AP_WIN) {
+        if (tid == 0) q_n = 0;
+        __syncthreads();
+        if (vec && w0 + AP_WIN <= total) {
+            const int4* c4 = reinterpret_cast<const int4*>(cand + w0);
+            const int4 u = c4[tid], v = c4[tid + AP_THREADS];
             if ((u.x & u.y & u.z & u.w) != -1) {
-                if (u.x != -1) apply_one(u.x, 4 * q, gtp, gt_off, tail, g, y, y2);
-                if (u.y != -1) apply_one(u.y, 4 * q + 1, gtp, gt_off, tail, g, y, y2);
-                if (u.z != -1) apply_one(u.z, 4 * q + 2, gtp, gt_off, tail, g, y, y2);
-                if (u.w != -1) apply_one(u.w, 4 * q + 3, gtp, gt_off, tail, g, y, y2);
+                if (u.x != -1) q_pos[atomicAdd(&q_n, 1)] = 4 * tid;
+                if (u.y != -1) q_pos[atomicAdd(&q_n, 1)] = 4 * tid + 1;
+                if (u.z != -1) q_pos[atomicAdd(&q_n, 1)] = 4 * tid + 2;
+                if (u.w != -1) q_pos[atomicAdd(&q_n, 1)] = 4 * tid + 3;
             }
             if ((v.x & v.y & v.z & v.w) != -1) {
-                const long long q2 = q + stride;
-                if (v.x != -1) apply_one(v.x, 4 * q2, gtp, gt_off, tail, g, y, y2);
-                if (v.y != -1) apply_one(v.y, 4 * q2 + 1, gtp, gt_off, tail, g, y, y2);
-                if (v.z != -1) apply_one(v.z, 4 * q2 + 2, gtp, gt_off, tail, g, y, y2);
-                if (v.w != -1) apply_one(v.w, 4 * q2 + 3, gtp, gt_off, tail, g, y, y2);
+                const int o = 4 * (tid + AP_THREADS);
+                if (v.x != -1) q_pos[atomicAdd(&q_n, 1)] = o;
+                if (v.y != -1) q_pos[atomicAdd(&q_n, 1)] = o + 1;
+                if (v.z != -1) q_pos[atomicAdd(&q_n, 1)] = o + 2;
+                if (v.w != -1) q_pos[atomicAdd(&q_n, 1)] = o + 3;
             }
+        } else {
+            for (int e = tid; e < AP_WIN && w0 + e < total; e += AP_THREADS)
+                if (cand[w0 + e] != -1) q_pos[atomicAdd(&q_n, 1)] = e;
         }
-        for (long long i = 4 * quads + t0; i < total; i += stride) {
-            const int c = cand[i];
-            if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
+        __syncthreads();
+        const int n = q_n;
+        for (int e = tid; e < n; e += AP_THREADS) {
+            const long long i = w0 + q_pos[e];
+            apply_one(cand[i], i, gtp, gt_off, tail, g, y, y2);
         }
-    } else {
-        for (long long i = t0; i < total; i += stride) {
-            const int c = cand[i];
-            if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
-        }
+        __syncthreads();
     }
 }
 
@@ -1187,6 +1391,7 @@ struct ShapeClasses {
     std::vector<int> grp_cls;           // group of 32 slots -> class
     std::vector<float> grp_box;         // group -> x0, y0, x1, y1 of a box around all its anchors (rounded outward)
     std::vector<float> cls;             // K x 4: w_up, h_up, area_lo, 0
+    std::vector<int> cls_goff;          // K + 1: first group of every class
     int K = 0;
 };
 
@@ -1246,6 +1451,8 @@ static bool build_shape_classes(const std::vector<Box<double>>& ab, ShapeClasses
         out->perm[start[i] + fill[i]++] = a;
     }
     const int G = start[K] / 32;
+    out->cls_goff.resize(K + 1);
+    for (int i = 0; i <= K; ++i) out->cls_goff[i] = start[i] / 32;
     out->grp_box.assign((size_t)G * 4, 0.f);
     for (int gidx = 0; gidx < G; ++gidx) {
         float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
@@ -1304,7 +1511,8 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     const bool no_overlap = getenv("SSDC_ENC_NO_OVERLAP") != nullptr;      // (diagnostic switches, read per call)
     const size_t smem_tpl = (size_t)ET_ROWS * row_bytes * (y2_dev ? 2 : 1);
     const bool overlap = tma_ok && !no_overlap && smem_tpl <= 64 * 1024;
-    if (overlap) {
+    const int dbg = getenv("SSDC_ENC_DBG") ? atoi(getenv("SSDC_ENC_DBG")) : 0;      // (timing experiments only)
+    if (overlap && dbg != 1) {
         // E3 template stream: independent of the ground truth, so it starts first and runs beside E1 / E2.
         // (With per-launch profiling on, everything stays on the main stream so that each kernel is timed alone.)
         cudaStream_t ts = ctx->profile ? st : d->stream2;
@@ -1343,39 +1551,67 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         if (!cand) { SSDC_TRY(d->matches.ensure((size_t)total * sizeof(int))); cand = d->matches.as<int>(); }
         if (n_gt > 0 || midx_dev) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
         if (n_gt > 0) {
-            SSDC_TRY(d->partial.ensure((size_t)n_gt * sizeof(int)));
-            match = d->partial.as<int>();
+            const ssdc_encoder::PerDev& pd = enc->dev[slot];
+            FastArgs f;
+            f.perm = pd.f_perm.as<int>(); f.pbox = pd.f_box.as<Box<double>>(); f.pboxf = pd.f_boxf.as<float4>();
+            f.grp_cls = pd.f_grpcls.as<int>(); f.grp_box = pd.f_grpbox.as<float4>(); f.cls = pd.f_cls.as<float4>(); f.cls_goff = pd.f_clsgoff.as<int>(); f.n_slots = enc->f_slots; f.K = enc->f_classes;
+            const int ngroups = f.n_slots / 32;
+            // CTAs per image: enough CTAs to fill the device a few times over, at least one group per warp and step
+            int nblk = (int)((6LL * d->sm_count + B - 1) / B);
+            if (const char* e = getenv("SSDC_ENC_NBLK")) nblk = atoi(e);
+            if (nblk > ngroups / (EP_THREADS / 32)) nblk = ngroups / (EP_THREADS / 32);
+            if (nblk > 16) nblk = 16;
+            if (nblk < 1) nblk = 1;
+            size_t off = 0;
+            auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+            const size_t o_mt = carve((size_t)n_gt * sizeof(int));
+            const size_t o_cnt = carve((size_t)n_gt * sizeof(int));
+            const size_t o_irr = carve((size_t)B * sizeof(int));
+            const size_t o_tau = carve((size_t)n_gt * sizeof(float));
+            const size_t o_lv = carve((size_t)n_gt * EL_CAP * sizeof(double));
+            const size_t o_li = carve((size_t)n_gt * EL_CAP * sizeof(int));
+            SSDC_TRY(d->partial.ensure(off));
+            char* base = d->partial.as<char>();
+            match = reinterpret_cast<int*>(base + o_mt);
+            int* lcnt = reinterpret_cast<int*>(base + o_cnt);
+            int* img_irr = reinterpret_cast<int*>(base + o_irr);
+            float* gtau = reinterpret_cast<float*>(base + o_tau);
+            double* lval = reinterpret_cast<double*>(base + o_lv);
+            int* lidx = reinterpret_cast<int*>(base + o_li);
+            SSDC_CUDA(cudaMemsetAsync(base + o_cnt, 0, (o_irr - o_cnt) + (size_t)B * sizeof(int), st));     // lcnt, img_irr
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
                 gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
                 SSDC_TRY(check_launch("gt_prep_kernel"));
             }
             {
+                LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
+                seed_kernel<<<(unsigned)((n_gt + 7) / 8), 256, 0, st>>>(gtp, (int)n_gt, f, gtau);
+                SSDC_TRY(check_launch("seed_kernel"));
+            }
+            {
+                LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
+                const size_t mm = ((size_t)max_m + 1) & ~(size_t)1;
+                const size_t smem = mm * (sizeof(Box<double>) + sizeof(float4) + 3 * sizeof(float) + sizeof(int)) + mm * f.K * sizeof(float) + EF_MAX_K * sizeof(float) + 32;
+                dim3 grid((unsigned)nblk, (unsigned)B);
+                SSDC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pair_kernel<<<grid, EP_THREADS, smem, st>>>(gtp, gt_off, f, g, gtau, cand, lcnt, lval, lidx, img_irr);
+                SSDC_TRY(check_launch("pair_kernel"));
+            }
+            {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
-                const ssdc_encoder::PerDev& pd = enc->dev[slot];
-                FastArgs f;
-                f.perm = pd.f_perm.as<int>(); f.pbox = pd.f_box.as<Box<double>>(); f.pboxf = pd.f_boxf.as<float4>();
-                f.grp_cls = pd.f_grpcls.as<int>(); f.grp_box = pd.f_grpbox.as<float4>(); f.cls = pd.f_cls.as<float4>(); f.n_slots = enc->f_slots; f.K = enc->f_classes;
-                const size_t mm = (size_t)max_m;
-                const size_t smem = mm * (sizeof(Box<double>) + sizeof(double) + sizeof(float4)) + mm * f.K * sizeof(float) +
-                                    mm * (4 * sizeof(int) + 1) + 32;
-                const int T = (B >= 2 * d->sm_count) ? 256 : 512;
-                if (max_m <= 32) {
-                    SSDC_CUDA(cudaFuncSetAttribute(pairmatch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pairmatch_kernel<1><<<(unsigned)B, T, smem, st>>>(gtp, gt_off, f, g, cand, match);
-                } else {
-                    SSDC_CUDA(cudaFuncSetAttribute(pairmatch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pairmatch_kernel<4><<<(unsigned)B, T, smem, st>>>(gtp, gt_off, f, g, cand, match);
-                }
-                SSDC_TRY(check_launch("pairmatch_kernel"));
+                const size_t smem = (size_t)(ngroups + f.K) * sizeof(float4) + (size_t)max_m * (sizeof(double) + 4 * sizeof(int)) + (f.K + 1 + 2 * (size_t)ngroups) * sizeof(int) + 16;
+                SSDC_CUDA(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                greedy_kernel<<<(unsigned)B, EG_WARPS * 32, smem, st>>>(gtp, gt_off, f, g, gtau, lcnt, lval, lidx, img_irr, cand, match);
+                SSDC_TRY(check_launch("greedy_kernel"));
             }
         }
-        if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
-        if (n_gt > 0) {
+        if (!ctx->profile && dbg != 1) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+        if (n_gt > 0 && dbg != 2) {
             LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
-            long long blocks = (total / 8 + 255) / 256 + 1;
-            if (blocks > (long long)d->sm_count * 16) blocks = (long long)d->sm_count * 16;
-            apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, gtp, gt_off, tail, g, total, y_dev, y2_dev);
+            long long blocks = (total + AP_WIN - 1) / AP_WIN;
+            if (blocks > (long long)d->sm_count * 8) blocks = (long long)d->sm_count * 8;
+            apply_kernel<<<(unsigned)blocks, AP_THREADS, 0, st>>>(cand, gtp, gt_off, tail, g, total, y_dev, y2_dev);
             SSDC_TRY(check_launch("apply_kernel"));
         }
         return SSDC_OK;
@@ -1508,11 +1744,13 @@ int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const d
             if (r == SSDC_OK) r = pd.f_boxf.ensure(S * sizeof(float4));
             if (r == SSDC_OK) r = pd.f_grpcls.ensure(sc.grp_cls.size() * sizeof(int));
             if (r == SSDC_OK) r = pd.f_grpbox.ensure(sc.grp_box.size() * sizeof(float));
+            if (r == SSDC_OK) r = pd.f_clsgoff.ensure(sc.cls_goff.size() * sizeof(int));
             if (r == SSDC_OK) r = pd.f_cls.ensure(sc.cls.size() * sizeof(float));
             if (r == SSDC_OK &&
                 (cudaMemcpy(pd.f_perm.p, sc.perm.data(), S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
                  cudaMemcpy(pd.f_grpcls.p, sc.grp_cls.data(), sc.grp_cls.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
                  cudaMemcpy(pd.f_grpbox.p, sc.grp_box.data(), sc.grp_box.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                 cudaMemcpy(pd.f_clsgoff.p, sc.cls_goff.data(), sc.cls_goff.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
                  cudaMemcpy(pd.f_cls.p, sc.cls.data(), sc.cls.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)) r = SSDC_ERR_CUDA;
             if (r == SSDC_OK) {
                 LaunchScope ls(ctx, &d, SSDC_K_THIN);
@@ -1525,7 +1763,7 @@ int ssdc_encoder_create(ssdc_ctx* ctx, const double* anchors, int64_t A, const d
         if (r != SSDC_OK) {
             for (auto& pd : enc->dev) {
                 pd.anchor_box.release(); pd.anchor_tail.release(); pd.anchor_boxf.release();
-                pd.f_perm.release(); pd.f_box.release(); pd.f_boxf.release(); pd.f_grpcls.release(); pd.f_grpbox.release(); pd.f_cls.release();
+                pd.f_perm.release(); pd.f_box.release(); pd.f_boxf.release(); pd.f_grpcls.release(); pd.f_grpbox.release(); pd.f_cls.release(); pd.f_clsgoff.release();
             }
             delete enc;
             return r;
@@ -1544,7 +1782,7 @@ void ssdc_encoder_destroy(ssdc_encoder* enc) {
         enc->dev[i].anchor_tail.release();
         enc->dev[i].anchor_boxf.release();
         enc->dev[i].f_perm.release(); enc->dev[i].f_box.release(); enc->dev[i].f_boxf.release();
-        enc->dev[i].f_grpcls.release(); enc->dev[i].f_grpbox.release(); enc->dev[i].f_cls.release();
+        enc->dev[i].f_grpcls.release(); enc->dev[i].f_grpbox.release(); enc->dev[i].f_cls.release(); enc->dev[i].f_clsgoff.release();
     }
     delete enc;
 }
