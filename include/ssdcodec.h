@@ -97,9 +97,10 @@ int64_t ssdc_launch_count(const ssdc_ctx* ctx);
 #define SSDC_K_MERGE         4   /* D4  cross-class top-k + output packing           */
 #define SSDC_K_ENC_ROWBEST   5   /* E1  GT x anchor IoU, per-GT best anchor          */
 #define SSDC_K_ENC_MATCH     6   /* E2  bipartite greedy rounds                      */
-#define SSDC_K_ENC_WRITE     7   /* E3  multi-match + neutral + offsets + write-out  */
+#define SSDC_K_ENC_WRITE     7   /* E3  y_encoded write-out (template stream, or the fused write kernel) */
 #define SSDC_K_THIN          8   /*     standalone iou / convert / match ops         */
-#define SSDC_K_COUNT         9
+#define SSDC_K_ENC_PATCH     9   /* E3' rows of matched / neutral anchors patched into the streamed template */
+#define SSDC_K_COUNT         10
 int ssdc_profile_enable(ssdc_ctx* ctx, int on);
 int ssdc_profile_read(ssdc_ctx* ctx, double* ms /*SSDC_K_COUNT*/, int64_t* launches /*SSDC_K_COUNT*/);
 

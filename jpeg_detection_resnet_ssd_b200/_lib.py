@@ -23,7 +23,7 @@ MODE_PER_CLASS, MODE_FAST, MODE_LAYER, MODE_LAYER_FAST = 0, 1, 2, 3
 CONVERSIONS = {'minmax2centroids': 0, 'centroids2minmax': 1, 'corners2centroids': 2,
                'centroids2corners': 3, 'minmax2corners': 4, 'corners2minmax': 5}
 IOU_OUTER, IOU_ELEMENTWISE = 0, 1
-K_NAMES = ['decode_filter', 'plan', 'sort', 'nms', 'merge', 'enc_rowbest', 'enc_match', 'enc_write', 'thin']
+K_NAMES = ['decode_filter', 'plan', 'sort', 'nms', 'merge', 'enc_rowbest', 'enc_match', 'enc_write', 'thin', 'enc_patch']
 K_COUNT = len(K_NAMES)
 
 

@@ -904,13 +904,15 @@ constexpr float EL_FRAC = 0.7f;               // tau_r = EL_FRAC * (best IoU ins
 // Seed: one warp per ground-truth row evaluates the class with the largest shape bound (where the row's
 // best anchor usually lives) exactly and derives tau_r from the best IoU found there.  Any tau_r > 0 is
 // valid; this choice keeps the lists short (a few dozen entries) and almost never dry.
-__global__ void __launch_bounds__(256)
+constexpr int ES_WARPS = 4;
+__global__ void __launch_bounds__(ES_WARPS * 32)
 seed_kernel(const GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restrict__ gtau) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_gt) return;
+    __shared__ int s_cut;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x;
     const GtPrep* gp = gtp + row;
-    if (!gp->regular) { if (lane == 0) gtau[row] = 0.f; return; }
+    if (!gp->regular) { if (threadIdx.x == 0) gtau[row] = 0.f; return; }
+    if (threadIdx.x == 0) s_cut = 0;
     const int K = f.K;
     const float u0 = (lane < K) ? shape_bound(gp, f.cls[lane]) : -1.f;
     const float u1 = (lane + 32 < K) ? shape_bound(gp, f.cls[lane + 32]) : -1.f;
@@ -926,14 +928,17 @@ seed_kernel(const GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restr
     const float4 gf = gp->sf;
     const float garea = gp->area_lo, carea = f.cls[bk].z;
     const int ge = f.cls_goff[bk + 1];
+    __syncthreads();
     float cut = 0.f;
     for (int gb0 = f.cls_goff[bk]; gb0 < ge; gb0 += 32) {
         const int gl = gb0 + lane;
         const bool want = (gl < ge) && !screen_disjoint(gf, f.grp_box[gl]);
         unsigned gm = __ballot_sync(0xffffffffu, want);
+        int nth = 0;
         while (gm) {
             const int gidx = gb0 + __ffs(gm) - 1;
             gm &= gm - 1;
+            if ((nth++ % ES_WARPS) != warp) continue;           // the groups that meet the row, dealt to the warps in turn
             const int slot = gidx * 32 + lane;
             const int a = f.perm[slot];
             const float4 af = f.pboxf[slot];
@@ -945,7 +950,9 @@ seed_kernel(const GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restr
             cut = fmaxf(cut, __int_as_float(c));
         }
     }
-    if (lane == 0) gtau[row] = __fmul_rd(cut, EL_FRAC);
+    if (lane == 0 && cut > 0.f) atomicMax(&s_cut, __float_as_int(cut));
+    __syncthreads();
+    if (threadIdx.x == 0) gtau[row] = __fmul_rd(__int_as_float(s_cut), EL_FRAC);
 }
 
 // E1 of the sparse path.  Grid (nblk, B): CTA (j, b) visits the 32-slot groups j, j + nblk, ... of image b,
@@ -958,7 +965,8 @@ constexpr int EP_THREADS = 256;
 __global__ void __launch_bounds__(EP_THREADS, 4)
 pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
             const float* __restrict__ gtau, int* __restrict__ cand, int* __restrict__ lcnt,
-            double* __restrict__ lval, int* __restrict__ lidx, int* __restrict__ img_irr) {
+            double* __restrict__ lval, int* __restrict__ lidx, int* __restrict__ img_irr,
+            int* __restrict__ plist, int* __restrict__ pcount) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.y, nblk = gridDim.x, blk = blockIdx.x;
     const long long g0 = gt_off[b];
@@ -1054,11 +1062,17 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
                 }
             }
         }
-        if (live) {
-            const bool pos = g.multi && (cv >= g.pos_thr);          // matching_utils.py:109-114
-            const bool neu = cv >= g.neg_thr;                        // ssd_input_encoder.py:388-390
-            if (pos) cand[(size_t)b * g.A + a] = cg;
-            else if (neu) cand[(size_t)b * g.A + a] = -2;
+        const bool pos = live && g.multi && (cv >= g.pos_thr);      // matching_utils.py:109-114
+        const bool neu = live && (cv >= g.neg_thr);                  // ssd_input_encoder.py:388-390
+        if (pos) cand[(size_t)b * g.A + a] = cg;
+        else if (neu) cand[(size_t)b * g.A + a] = -2;
+        // positions that differ from the template, for the patch kernel
+        const unsigned wm = __ballot_sync(0xffffffffu, pos || neu);
+        if (wm && plist) {
+            int basep = 0;
+            if (lane == 0) basep = atomicAdd(pcount, __popc(wm));
+            basep = __shfl_sync(0xffffffffu, basep, 0);
+            if (pos || neu) plist[basep + __popc(wm & ((1u << lane) - 1u))] = (int)((long long)b * g.A + a);
         }
     }
     if (__any_sync(0xffffffffu, irr) && lane == 0) atomicOr(&img_irr[b], 1);
@@ -1092,7 +1106,8 @@ __device__ __forceinline__ void list_best(const double* __restrict__ lval, const
 __global__ void __launch_bounds__(EG_WARPS * 32)
 greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off, FastArgs f, EncArgs g,
               const float* __restrict__ gtau, const int* __restrict__ lcnt, const double* __restrict__ lval, const int* __restrict__ lidx,
-              const int* __restrict__ img_irr, int* __restrict__ cand, int* __restrict__ match) {
+              const int* __restrict__ img_irr, int* __restrict__ cand, int* __restrict__ match,
+              int* __restrict__ plist, int* __restrict__ pcount) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red_val[EG_WARPS];
     __shared__ int red_idx[EG_WARPS];
@@ -1306,8 +1321,14 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
         __syncthreads();
         if (!s_more) break;
     }
-    if (tid == 0)
-        for (int r = 0; r < m; ++r) cand[(size_t)b * g.A + match[g0 + r]] = r;
+    if (tid == 0) {
+        const int basep = plist ? atomicAdd(pcount, m) : 0;
+        for (int r = 0; r < m; ++r) {
+            const long long pos = (long long)b * g.A + match[g0 + r];
+            cand[pos] = r;
+            if (plist) plist[basep + r] = (int)pos;
+        }
+    }
 }
 
 
@@ -1330,10 +1351,15 @@ __device__ __forceinline__ void apply_one(int c, long long i, const GtPrep* __re
         for (int k = 0; k < 4; ++k) dst[C + k] = off[k];
         cls = gp.cls;
     }
-    for (int k = 0; k < C; ++k) dst[k] = (k == cls) ? 1.0 : 0.0;
-    if (y2) {
-        double* dst2 = y2 + (size_t)i * W;
-        for (int k = 0; k < C; ++k) dst2[k] = (k == cls) ? 1.0 : 0.0;
+    // class vector: the template row is one-hot background; only the columns that change are written
+    if (cls != g.background_id) {
+        dst[g.background_id] = 0.0;
+        if (cls >= 0) dst[cls] = 1.0;
+        if (y2) {
+            double* dst2 = y2 + (size_t)i * W;
+            dst2[g.background_id] = 0.0;
+            if (cls >= 0) dst2[cls] = 1.0;
+        }
     }
 }
 
@@ -1379,6 +1405,19 @@ apply_kernel(const int* __restrict__ cand, const GtPrep* __restrict__ gtp, const
             apply_one(cand[i], i, gtp, gt_off, tail, g, y, y2);
         }
         __syncthreads();
+    }
+}
+
+// the same over the list of positions pair_kernel / greedy_kernel recorded (duplicates are harmless: same row, same values)
+__global__ void __launch_bounds__(128)
+apply_list_kernel(const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ cand,
+                  const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
+                  const double* __restrict__ tail, EncArgs g, double* __restrict__ y, double* __restrict__ y2) {
+    const int n = *pcount;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const long long i = plist[e];
+        const int c = cand[i];
+        if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
     }
 }
 
@@ -1550,6 +1589,9 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         int* cand = midx_dev;
         if (!cand) { SSDC_TRY(d->matches.ensure((size_t)total * sizeof(int))); cand = d->matches.as<int>(); }
         if (n_gt > 0 || midx_dev) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
+        const bool use_plist = total < 0x7fffffffLL && getenv("SSDC_ENC_DENSE_PATCH") == nullptr;
+        int* plist = nullptr;
+        int* pcount = nullptr;
         if (n_gt > 0) {
             const ssdc_encoder::PerDev& pd = enc->dev[slot];
             FastArgs f;
@@ -1566,10 +1608,11 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
             const size_t o_mt = carve((size_t)n_gt * sizeof(int));
             const size_t o_cnt = carve((size_t)n_gt * sizeof(int));
-            const size_t o_irr = carve((size_t)B * sizeof(int));
+            const size_t o_irr = carve((size_t)B * sizeof(int) + sizeof(int));       // + the position counter
             const size_t o_tau = carve((size_t)n_gt * sizeof(float));
             const size_t o_lv = carve((size_t)n_gt * EL_CAP * sizeof(double));
             const size_t o_li = carve((size_t)n_gt * EL_CAP * sizeof(int));
+            const size_t o_pl = use_plist ? carve((size_t)total * sizeof(int)) : 0;
             SSDC_TRY(d->partial.ensure(off));
             char* base = d->partial.as<char>();
             match = reinterpret_cast<int*>(base + o_mt);
@@ -1578,7 +1621,9 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             float* gtau = reinterpret_cast<float*>(base + o_tau);
             double* lval = reinterpret_cast<double*>(base + o_lv);
             int* lidx = reinterpret_cast<int*>(base + o_li);
-            SSDC_CUDA(cudaMemsetAsync(base + o_cnt, 0, (o_irr - o_cnt) + (size_t)B * sizeof(int), st));     // lcnt, img_irr
+            pcount = img_irr + B;
+            plist = use_plist ? reinterpret_cast<int*>(base + o_pl) : nullptr;
+            SSDC_CUDA(cudaMemsetAsync(base + o_cnt, 0, (o_irr - o_cnt) + (size_t)(B + 1) * sizeof(int), st));     // lcnt, img_irr, pcount
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
                 gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
@@ -1586,7 +1631,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             }
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
-                seed_kernel<<<(unsigned)((n_gt + 7) / 8), 256, 0, st>>>(gtp, (int)n_gt, f, gtau);
+                seed_kernel<<<(unsigned)n_gt, ES_WARPS * 32, 0, st>>>(gtp, (int)n_gt, f, gtau);
                 SSDC_TRY(check_launch("seed_kernel"));
             }
             {
@@ -1595,24 +1640,29 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
                 const size_t smem = mm * (sizeof(Box<double>) + sizeof(float4) + 3 * sizeof(float) + sizeof(int)) + mm * f.K * sizeof(float) + EF_MAX_K * sizeof(float) + 32;
                 dim3 grid((unsigned)nblk, (unsigned)B);
                 SSDC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                pair_kernel<<<grid, EP_THREADS, smem, st>>>(gtp, gt_off, f, g, gtau, cand, lcnt, lval, lidx, img_irr);
+                pair_kernel<<<grid, EP_THREADS, smem, st>>>(gtp, gt_off, f, g, gtau, cand, lcnt, lval, lidx, img_irr, plist, pcount);
                 SSDC_TRY(check_launch("pair_kernel"));
             }
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
                 const size_t smem = (size_t)(ngroups + f.K) * sizeof(float4) + (size_t)max_m * (sizeof(double) + 4 * sizeof(int)) + (f.K + 1 + 2 * (size_t)ngroups) * sizeof(int) + 16;
                 SSDC_CUDA(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                greedy_kernel<<<(unsigned)B, EG_WARPS * 32, smem, st>>>(gtp, gt_off, f, g, gtau, lcnt, lval, lidx, img_irr, cand, match);
+                greedy_kernel<<<(unsigned)B, EG_WARPS * 32, smem, st>>>(gtp, gt_off, f, g, gtau, lcnt, lval, lidx, img_irr, cand, match, plist, pcount);
                 SSDC_TRY(check_launch("greedy_kernel"));
             }
         }
         if (!ctx->profile && dbg != 1) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
         if (n_gt > 0 && dbg != 2) {
-            LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
-            long long blocks = (total + AP_WIN - 1) / AP_WIN;
-            if (blocks > (long long)d->sm_count * 8) blocks = (long long)d->sm_count * 8;
-            apply_kernel<<<(unsigned)blocks, AP_THREADS, 0, st>>>(cand, gtp, gt_off, tail, g, total, y_dev, y2_dev);
-            SSDC_TRY(check_launch("apply_kernel"));
+            LaunchScope ls(ctx, d, SSDC_K_ENC_PATCH);
+            if (plist) {
+                apply_list_kernel<<<(unsigned)(d->sm_count * 8), 128, 0, st>>>(plist, pcount, cand, gtp, gt_off, tail, g, y_dev, y2_dev);
+                SSDC_TRY(check_launch("apply_list_kernel"));
+            } else {
+                long long blocks = (total + AP_WIN - 1) / AP_WIN;
+                if (blocks > (long long)d->sm_count * 8) blocks = (long long)d->sm_count * 8;
+                apply_kernel<<<(unsigned)blocks, AP_THREADS, 0, st>>>(cand, gtp, gt_off, tail, g, total, y_dev, y2_dev);
+                SSDC_TRY(check_launch("apply_kernel"));
+            }
         }
         return SSDC_OK;
     }
@@ -1666,7 +1716,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             // patch the rows of matched / neutral anchors once the template has landed
             if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
             if (n_gt == 0 && !midx_dev) return SSDC_OK;
-            LaunchScope ls(ctx, d, SSDC_K_ENC_WRITE);
+            LaunchScope ls(ctx, d, SSDC_K_ENC_PATCH);
             SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gt));
             write_tma_kernel<true><<<(unsigned)(B * tiles), E3_THREADS, smem_gt, st>>>(gtp, gt_off, abox, enc->dev[slot].anchor_boxf.as<float4>(), tail, match, g, tiles, y_dev, y2_dev, midx_dev);
             SSDC_TRY(check_launch("write_tma_kernel<patch>"));

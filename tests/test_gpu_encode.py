@@ -15,11 +15,14 @@ pytestmark = pytest.mark.gpu
 OFFSET_RTOL = 1e-5    # north_star: encoded offsets within 1e-5 relative
 
 
-@pytest.fixture(autouse=True, params=['sparse', 'general', 'serial'])
+@pytest.fixture(autouse=True, params=['sparse', 'sparse_dense_patch', 'general', 'serial'])
 def enc_path(request, monkeypatch):
-    """Every test runs through the three encoder pipelines: shape-class sparse path (default), the general
-    kernels beside the template stream, and the fully serial general kernels."""
-    if request.param != 'sparse':
+    """Every test runs through the encoder pipelines: shape-class sparse path (default; also with the patch
+    kernel that scans the dense decision array instead of the position list), the general kernels beside
+    the template stream, and the fully serial general kernels."""
+    if request.param == 'sparse_dense_patch':
+        monkeypatch.setenv('SSDC_ENC_DENSE_PATCH', '1')
+    elif request.param != 'sparse':
         monkeypatch.setenv('SSDC_ENC_GENERAL', '1')
     if request.param == 'serial':
         monkeypatch.setenv('SSDC_ENC_NO_OVERLAP', '1')
@@ -157,3 +160,22 @@ def test_encode_more_rows_than_sparse_path_takes(ctx):
     yo, mo = oenc(gt, return_matches=True)
     assert np.array_equal(mi, mo)
     assert rel_err(y, yo).max() <= OFFSET_RTOL
+
+
+def test_encode_bench_batch_vs_oracle(ctx, enc_path):
+    """The bench's round-trip batch (512 images, seed 78), every image against the oracle.  (One of these images
+    exposes a runner-up that lies in an anchor chunk / shape class which the first pass pruned against the
+    row's original best - the case test_encode_runner_up_in_other_class builds by hand.)"""
+    if enc_path == 'serial':
+        pytest.skip('same kernels as "general"')
+    kw = synth.layout_kwargs('ssd300')
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    gt = synth.synth_ground_truth(300, 300, 20, 512, seed=78)
+    y, mi = enc(gt, return_matches=True)
+    for i in range(len(gt)):
+        yo, mo = oenc([gt[i]], return_matches=True)
+        assert np.array_equal(mi[i], mo[0]), i
+        nz = np.nonzero(mo[0] != -1)[0]
+        assert np.array_equal(y[i][nz, :21], yo[0][nz, :21]), i
+        assert rel_err(y[i][nz], yo[0][nz]).max(initial=0.0) <= OFFSET_RTOL, i
