@@ -10,18 +10,27 @@
 // Kernels:
 //   anchor_prep_kernel : once per encoder: anchor corners + union area term, and the 12-double tail
 //                        [offsets | anchor | variances] every unmatched row carries (literal formula,
-//                        so 0/0 anchors still produce the reference's NaN).
+//                        so 0/0 anchors still produce the reference's NaN).  The host then groups the
+//                        anchors into shape classes (build_shape_classes) for the sparse path.
 //   gt_prep_kernel     : per ground-truth row: normalise, convert to the target coordinate format,
 //                        corner form for the IoU.
-//   E1 rowbest_kernel  : per (image, anchor chunk): IoU of every GT row with the chunk's anchors,
-//                        np.argmax-faithful (value, first index) reduction per GT row.
-//   E2 match_kernel    : one warp per image: reduces the chunk partials and runs the m greedy rounds
-//                        of match_bipartite_greedy literally (including the all-zero re-match quirk);
-//                        a row is rescanned only when its best column was taken.
-//   E3 write_kernel    : per (image, anchor tile): per-anchor best GT (match_multi), neutral test,
-//                        target offsets; the tile of y_encoded is generated element by element and
-//                        streamed out with fully coalesced stores.  The encoding template is never
-//                        materialised separately.
+//   E3 template_tma_kernel : streams y_encoded out (TMA bulk stores of per-anchor-range tiles that are
+//                        identical for every image) on a side stream, beside the matching.
+//   Sparse path (anchor sets with <= 64 shape classes, <= 128 rows per image, positive thresholds):
+//     seed_kernel      : per row: list level tau_r from the most promising shape class
+//     E1 pair_kernel   : thread <-> anchor; (row, class) shape bounds, group bounding boxes, float32
+//                        screens, exact float64 IoU for the rest; match_multi / neutral decision per
+//                        anchor, candidate list per row
+//     E2 greedy_kernel : CTA per image: the m rounds of match_bipartite_greedy literally (including the
+//                        all-zero re-match quirk) on the lists; cooperative rescan when a list runs dry
+//     E3' apply_list_kernel : patches the matched / neutral rows into the streamed template
+//   General path (everything else; also the reference point the sparse path is tested against):
+//     E1 rowbest_kernel: per (image, anchor chunk): best anchor of every GT row, np.argmax-faithful
+//     E2 match_kernel  : one CTA per image: chunk partials + greedy rounds; a row whose best column was
+//                        taken is rescanned in every chunk
+//     E3 write_tma_kernel<false> : decide + assemble + one TMA bulk store per 128-row tile (no side stream)
+//        write_tma_kernel<true>  : decide + patch after the template stream
+//        write_kernel  : element-wise fallback for unaligned tiles
 #include "common.cuh"
 #include "ctx.cuh"
 #include <math.h>
