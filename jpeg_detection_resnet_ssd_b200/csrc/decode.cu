@@ -39,6 +39,7 @@ template <typename T> struct alignas(16) SBox { T x0, y0, x1, y1; };
 
 struct DecodeArgs {
     int A, C, W, NS, tiles, tile_rows;
+    int dbg_null;                 // timing experiments only: consumers skip the tile (SSDC_D1_NULL)
     int input_coords, log_wh, layer_assoc, ge;
     int do_nms, K, Kseg, always_sort;
     double iou_thr, sx, sy, d;
@@ -314,15 +315,19 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
         return;
     }
     // ---- consumer warps ----
+    // (image / tile of the CTA's next tile by increments: no integer division per tile)
+    const int step_b = (int)gridDim.x / g.tiles, step_t = (int)gridDim.x - step_b * g.tiles;
+    int b = (int)blockIdx.x / g.tiles, tile_id = (int)blockIdx.x - b * g.tiles;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, b += step_b, tile_id += step_t) {
+        if (tile_id >= g.tiles) { tile_id -= g.tiles; ++b; }
         const int s = it % D1_STAGES;
         mbar_wait(&full[s], (uint32_t)((it / D1_STAGES) & 1));
-        const int b = t / g.tiles, tile_id = t - b * g.tiles;
         const int a0 = tile_id * g.tile_rows;
         const int rows = min(g.tile_rows, A - a0);
-        process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
-                                seg_count, keys, boxes, aux_class);
+        if (!g.dbg_null)
+            process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
+                                    seg_count, keys, boxes, aux_class);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);             // this warp is done with stage s
     }
@@ -1413,6 +1418,7 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
         if (ctas_per_sm > 4) ctas_per_sm = 4;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
+        if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only)
         const long long total_tiles = (long long)B * g.tiles;
         long long grid = (long long)d->sm_count * ctas_per_sm;
         if (grid > total_tiles) grid = total_tiles;
@@ -1642,6 +1648,7 @@ static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* 
     int rows = D1_THREADS;
     while (rows > 32 && ((size_t)rows * g.W + 4) * elem + 4096 > 100 * 1024) rows >>= 1;
     g.tile_rows = rows;
+    g.dbg_null = getenv("SSDC_D1_NULL") != nullptr;
     g.tiles = (int)((job.A + rows - 1) / rows);
     // float32 input stays float32 end to end only where the reference never upcasts:
     // input_coords == 'corners' (ssd_output_decoder.py:186-190) and the Keras layers.
