@@ -732,8 +732,8 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 //            class (lane <-> kept box, raw-corner disjointness), overlapping pairs are decided in
 //            batches (exact, division-free), warp 0 resolves the step and appends to the kept list.
 // ---------------------------------------------------------------------------
-constexpr int SW_THREADS = 256;
-constexpr int SW_WARPS = SW_THREADS / 32;
+// Threads per CTA (= per image) are a template parameter: 256 when all images fit one wave of 4 CTAs per
+// SM, else 128 (7 CTAs per SM: B = 1024 on 148 SMs is one wave instead of 1.7).
 constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
 constexpr int SW_TARGET = 288;          // the selection aims at >= this many (and <= SW_CHUNK)
 constexpr int SW_KMAX = 256;            // largest top_k the sweep path handles
@@ -742,11 +742,12 @@ constexpr int SW_QUEUE = 1024;          // per-warp pair queue (16-bit entries)
 __device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu - (unsigned)((k >> 24) & 0xffu)); }
 __device__ __forceinline__ unsigned ck_anchor(unsigned long long k) { return 0xffffffu - (unsigned)(k & 0xffffffu); }
 
-template <typename IouT, bool TF>
+template <typename IouT, bool TF, int SW_THREADS>
 __global__ void __launch_bounds__(SW_THREADS)
 sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
              const SBox<float>* __restrict__ boxes, DecodeArgs g,
              unsigned long long* __restrict__ final_keys, int* __restrict__ out_count) {
+    constexpr int SW_WARPS = SW_THREADS / 32;
     __shared__ unsigned long long ck[SW_CHUNK];                  // current chunk, sorted descending
     __shared__ unsigned long long kkey[SW_KMAX];                 // kept keys in keep order
     __shared__ SBox<float> kraw[SW_KMAX];                        // their raw corners
@@ -1458,9 +1459,17 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     SSDC_TRY(d->merge_scratch.ensure((size_t)B * g.K * sizeof(unsigned long long)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
-        sweep_kernel<IouT, TF><<<(unsigned)B, SW_THREADS, 0, st>>>(
-            d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
-            d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
+        // one image per CTA: 256 threads while every image is resident at once (4 CTAs per SM), else 128 (7 per SM)
+        bool narrow = B > 4LL * d->sm_count;
+        if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
+        if (narrow)
+            sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
+                d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
+        else
+            sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, 0, st>>>(
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
+                d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
         SSDC_TRY(check_launch("sweep_kernel"));
     }
     {

@@ -5,8 +5,9 @@ import numpy as np
 import bench
 from jpeg_detection_resnet_ssd_b200 import _lib
 _lib.LIB_PATH = os.environ.get('SSDC_LIB_AB', _lib.LIB_PATH)
-B = 1024
-y, cands, enc = bench.make_workload(B, 64, 8.0, seed=1234, pinned=False)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+bias = float(sys.argv[2]) if len(sys.argv) > 2 else 8.0
+y, cands, enc = bench.make_workload(B, 64, bias, seed=1234, pinned=False)
 ctx = _lib.get_context(); lib = ctx.lib
 d_y = ctx.dev_alloc(y.nbytes)
 _lib.check(lib.ssdc_memcpy_h2d(ctx.handle, 0, d_y, _lib.ptr(y), y.nbytes))
