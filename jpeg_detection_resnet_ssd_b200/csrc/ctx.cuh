@@ -80,6 +80,7 @@ struct DecodeJob {
     int C = 0, NS = 0, dtype = 0;
     ssdc_decode_params p;
     bool emitted = false;           // rows already written on the device
+    bool scan_pending = false;      // image-sweep path: padded rows are on the device, the packed row offsets are not computed yet
     int64_t out_capacity = 0;       // rows the device out buffer can hold
     int iou_f32 = 0;
 };
@@ -93,6 +94,7 @@ struct DevCtx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // decode scratch
     Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
+    Buf pad_rows, pad_anchor;        // image-sweep path: (B, top_k, 6) float64 rows + anchor ids, as the sweep leaves them
     PinnedBuf h_small;
     DecodeJob job;
     // encode scratch

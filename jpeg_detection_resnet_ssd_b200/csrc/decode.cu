@@ -13,7 +13,9 @@
 //                             decode of every anchor that produced a candidate (decode_filter_kernel: LDG
 //                             fallback for unaligned inputs).
 //   S  sweep_kernel         : hot configuration (finite top_k): per image radix-select + sort of the best
-//                             candidates and ONE descending class-aware NMS sweep that stops at top_k.
+//                             candidates and ONE descending class-aware NMS sweep that stops at top_k;
+//                             writes the final rows at (B, top_k, 6) stride.  scan_counts_kernel +
+//                             sweep_pack_kernel pack them for the host copy at collect time.
 //   general path (top_k='all', decode_detections_fast, float64 input, greedy_nms):
 //      plan_kernel          : bins the segments by size into device-side work lists.
 //   D2 sort_kernel          : segmented bitonic sort by (score desc, anchor asc), persistent CTAs.
@@ -746,7 +748,7 @@ template <typename IouT, bool TF, int SW_THREADS>
 __global__ void __launch_bounds__(SW_THREADS)
 sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
              const SBox<float>* __restrict__ boxes, DecodeArgs g,
-             unsigned long long* __restrict__ final_keys, int* __restrict__ out_count) {
+             double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
     constexpr int SW_WARPS = SW_THREADS / 32;
     __shared__ unsigned long long ck[SW_CHUNK];                  // current chunk, sorted descending
     __shared__ unsigned long long kkey[SW_KMAX];                 // kept keys in keep order
@@ -1017,23 +1019,33 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         __syncthreads();
     }
 
-    // ------------------------------------------------------------ final order
+    // ------------------------------------------------------------ final order, rows written in place
+    // The image's rows go to pad_rows[b, pos, :] = [class, conf, xmin, ymin, xmax, ymax] (float64, the layout of the
+    // reference's DecodeDetections layer output without the zero padding); packing for the host copy happens at
+    // collect time.
     const int nkept = s_nkept;
-    unsigned long long* fk = final_keys + (size_t)b * K;
-    if (nkept >= K || g.always_sort) {
-        // truncated (or layer mode): descending score, the sweep order
-        for (int i = tid; i < nkept; i += SW_THREADS) fk[i] = kkey[i];
-    } else {
-        // nothing truncated: classes ascending, inside a class the keep order (:212-218)
-        for (int i = tid; i < nkept; i += SW_THREADS) {
-            const int c = kcls[i];
-            int pos = 0;
+    const bool sweep_order = nkept >= K || g.always_sort;       // truncated (or layer mode): descending score, the sweep order
+    for (int i = tid; i < nkept; i += SW_THREADS) {
+        int pos = i;
+        const int c = kcls[i];
+        if (!sweep_order) {
+            // nothing truncated: classes ascending, inside a class the keep order (:212-218)
+            pos = 0;
             for (int j = 0; j < nkept; ++j) {
                 const int cj = kcls[j];
                 pos += (cj < c) || (cj == c && j < i);
             }
-            fk[pos] = kkey[i];
         }
+        const unsigned long long k = kkey[i];
+        const SBox<float> s = kraw[i];
+        double* o = pad_rows + ((size_t)b * K + pos) * 6;
+        o[0] = (double)c;
+        o[1] = (double)unord32((uint32_t)(k >> 32));
+        o[2] = (double)((IouT)s.x0 * sx);
+        o[3] = (double)((IouT)s.y0 * sy);
+        o[4] = (double)((IouT)s.x1 * sx);
+        o[5] = (double)((IouT)s.y1 * sy);
+        pad_anchor[(size_t)b * K + pos] = (int)ck_anchor(k);
     }
     if (tid == 0) out_count[b] = nkept;
 }
@@ -1142,20 +1154,16 @@ __device__ __forceinline__ void write_row(double* __restrict__ rows, int* __rest
     anchors[r] = (int)anchor;
 }
 
-template <typename IouT>
-__global__ void __launch_bounds__(64)
-sweep_emit_kernel(const unsigned long long* __restrict__ final_keys, const int* __restrict__ out_count,
-                  const long long* __restrict__ row_offset, const SBox<float>* __restrict__ boxes, DecodeArgs g,
-                  double* __restrict__ rows, int* __restrict__ anchors) {
+// image-sweep path, collect time: padded rows -> packed rows
+__global__ void __launch_bounds__(128)
+sweep_pack_kernel(const double* __restrict__ pad_rows, const int* __restrict__ pad_anchor, const int* __restrict__ out_count,
+                  const long long* __restrict__ row_offset, int K, double* __restrict__ rows, int* __restrict__ anchors) {
     const int b = blockIdx.x;
     const int cnt = out_count[b];
     const long long off = row_offset[b];
-    const SBox<float>* bx = boxes + (size_t)b * g.A;
-    const IouT sx = (IouT)g.sx, sy = (IouT)g.sy;
-    for (int r = threadIdx.x; r < cnt; r += 64) {
-        const unsigned long long k = final_keys[(size_t)b * g.K + r];
-        write_row<float, IouT>(rows, anchors, off + r, ck_cls(k), (double)unord32((uint32_t)(k >> 32)), ck_anchor(k), bx, sx, sy);
-    }
+    const double* src = pad_rows + (size_t)b * K * 6;
+    for (int e = threadIdx.x; e < cnt * 6; e += 128) rows[off * 6 + e] = src[e];
+    for (int r = threadIdx.x; r < cnt; r += 128) anchors[off + r] = pad_anchor[(size_t)b * K + r];
 }
 
 constexpr int EMIT_THREADS = 256;
@@ -1456,7 +1464,8 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     int* img_count = ints + L.seg_count;            // one counter per image (first B entries)
     cudaStream_t st = d->stream;
     SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, false, img_count, d->keys.as<KeyT>(), d->boxes.as<SBox<InT>>(), nullptr));
-    SSDC_TRY(d->merge_scratch.ensure((size_t)B * g.K * sizeof(unsigned long long)));
+    SSDC_TRY(d->pad_rows.ensure((size_t)B * g.K * 6 * sizeof(double)));
+    SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
         // one image per CTA: 256 threads while every image is resident at once (4 CTAs per SM), else 128 (7 per SM)
@@ -1465,18 +1474,14 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         if (narrow)
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
-                d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
+                d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         else
             sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, 0, st>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
-                d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>());
+                d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         SSDC_TRY(check_launch("sweep_kernel"));
     }
-    {
-        LaunchScope ls(ctx, d, SSDC_K_MERGE);
-        scan_counts_kernel<<<1, 1024, 0, st>>>(d->out_count.as<int>(), (int)B, d->row_offset.as<long long>());
-        SSDC_TRY(check_launch("scan_counts_kernel"));
-    }
+    // (the packed row offsets are only needed for the host copy: scan_counts_kernel runs at collect time)
     return SSDC_OK;
 }
 
@@ -1593,10 +1598,10 @@ static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
     const int Kcap = (g.Kseg > 0) ? min(g.Kseg, g.A) : g.A;
     LaunchScope ls(ctx, d, SSDC_K_MERGE);
     if (g.sweep) {
-        sweep_emit_kernel<IouT><<<(unsigned)B, 64, 0, d->stream>>>(
-            d->merge_scratch.as<unsigned long long>(), d->out_count.as<int>(), d->row_offset.as<long long>(),
-            reinterpret_cast<const SBox<float>*>(d->boxes.p), g, d->out_rows.as<double>(), d->out_anchor.as<int>());
-        SSDC_TRY(check_launch("sweep_emit_kernel"));
+        sweep_pack_kernel<<<(unsigned)B, 128, 0, d->stream>>>(
+            d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>(), d->row_offset.as<long long>(), g.K,
+            d->out_rows.as<double>(), d->out_anchor.as<int>());
+        SSDC_TRY(check_launch("sweep_pack_kernel"));
         return SSDC_OK;
     }
     if (g.NS <= 32 * MERGE_Q_MAX && g.A < (1 << 24) && g.C <= 256) {
@@ -1708,7 +1713,8 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     }
     SSDC_TRY(r);
 
-    if (g.K > 0) {
+    job.scan_pending = g.sweep != 0;
+    if (g.K > 0 && !g.sweep) {
         // bounded output: rows can be emitted right away without knowing the total
         job.out_capacity = B * (int64_t)g.K;
         SSDC_TRY(d->out_rows.ensure((size_t)job.out_capacity * 6 * sizeof(double)));
@@ -1726,12 +1732,17 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
 
 // Waits for the device, returns the number of result rows of this shard.
 int decode_finish_dev(ssdc_ctx* ctx, DevCtx* d, int64_t* total_rows) {
-    (void)ctx;
     DecodeJob& job = d->job;
     *total_rows = 0;
     if (!job.valid) { set_error("ssdc_decode_collect without a submitted decode"); return SSDC_ERR_STATE; }
     if (job.B == 0) return SSDC_OK;
     SSDC_CUDA(cudaSetDevice(d->device));
+    if (job.scan_pending) {
+        LaunchScope ls(ctx, d, SSDC_K_MERGE);
+        scan_counts_kernel<<<1, 1024, 0, d->stream>>>(d->out_count.as<int>(), (int)job.B, d->row_offset.as<long long>());
+        SSDC_TRY(check_launch("scan_counts_kernel"));
+        job.scan_pending = false;
+    }
     long long total = 0;
     SSDC_CUDA(cudaMemcpyAsync(&total, d->row_offset.as<long long>() + job.B, sizeof(long long), cudaMemcpyDeviceToHost, d->stream));
     SSDC_CUDA(cudaStreamSynchronize(d->stream));
