@@ -483,7 +483,51 @@ def extra_numbers(ctx, _lib, enc, peak):
         'decode_filter_ms': d1, 'decode_filter_frac_of_hbm_peak': B * A * 33 * 4 / (d1 / 1e3) / 1e9 / peak,
         'kernel_ms': {k: round(v[0] / 3, 4) for k, v in prof.items() if v[1]}}
     ctx.dev_free(d_y)
+
+    # the VOC matching core of the Evaluator (the consumer of the decoder's output)
+    try:
+        out['voc_match_predictions'] = voc_numbers(ctx)
+    except Exception as exc:      # secondary number: never take the headline down
+        out['voc_match_predictions'] = {'error': repr(exc)[:200]}
     return out
+
+
+def voc_numbers(ctx):
+    """`Evaluator.match_predictions` on a synthetic dataset (1000 images, 20 classes, 60 detections per image):
+    the public call with the reference's list-of-tuples structure, the device part alone, and the oracle's
+    per-prediction Python loop on the same data."""
+    from oracle import cases
+    from oracle import voc_eval_oracle as voc
+    from jpeg_detection_resnet_ssd_b200.eval_utils.average_precision_evaluator import Evaluator
+
+    case = dict(name='bench', seed=2024, n_images=1000, n_classes=20, dets_per_image=60, kwargs=dict())
+    inp = cases.build_voc_input(case)
+
+    class DS(object):
+        pass
+    ds = DS()
+    ds.labels, ds.image_ids, ds.eval_neutral = inp['labels'], inp['image_ids'], None
+    ev = Evaluator(model=None, n_classes=20, data_generator=ds)
+    ev.set_predictions(inp['prediction_results'])
+    n_pred = sum(len(p) for p in inp['prediction_results'])
+    ev.match_predictions(sorting_algorithm='mergesort')
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        ev.match_predictions(sorting_algorithm='mergesort')
+    t_api = (time.perf_counter() - t0) / reps
+    ctx.profile_enable(True)
+    ev.match_predictions(sorting_algorithm='mergesort')
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    dev_ms = prof['thin'][0]
+    t0 = time.perf_counter()
+    voc.match_predictions(inp['prediction_results'], inp['labels'], inp['image_ids'], None, 20, sorting_algorithm='mergesort')
+    t_cpu = time.perf_counter() - t0
+    return {'predictions': n_pred, 'api_predictions_per_s': n_pred / t_api, 'api_ms': t_api * 1e3,
+            'device_kernels_ms': dev_ms, 'device_predictions_per_s': n_pred / (dev_ms / 1e3),
+            'cpu_port_predictions_per_s': n_pred / t_cpu, 'cpu_port_s': t_cpu,
+            'note': 'api = Evaluator.match_predictions incl. flattening the list-of-tuples input in Python and the copies'}
 
 
 if __name__ == '__main__':
