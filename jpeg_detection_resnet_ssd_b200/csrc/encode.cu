@@ -1621,7 +1621,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             const size_t o_tau = carve((size_t)n_gt * sizeof(float));
             const size_t o_lv = carve((size_t)n_gt * EL_CAP * sizeof(double));
             const size_t o_li = carve((size_t)n_gt * EL_CAP * sizeof(int));
-            const size_t o_pl = use_plist ? carve((size_t)total * sizeof(int)) : 0;
+            const size_t o_pl = use_plist ? carve((size_t)(total + n_gt) * sizeof(int)) : 0;      // every anchor once + the bipartite matches
             SSDC_TRY(d->partial.ensure(off));
             char* base = d->partial.as<char>();
             match = reinterpret_cast<int*>(base + o_mt);

@@ -179,3 +179,23 @@ def test_encode_bench_batch_vs_oracle(ctx, enc_path):
         nz = np.nonzero(mo[0] != -1)[0]
         assert np.array_equal(y[i][nz, :21], yo[0][nz, :21]), i
         assert rel_err(y[i][nz], yo[0][nz]).max(initial=0.0) <= OFFSET_RTOL, i
+
+
+@pytest.mark.parametrize('layout', ['tiny', 'ssd300'])
+def test_encode_low_thresholds_everything_matches(ctx, layout):
+    """IoU thresholds close to zero: almost every anchor is a positive match, the per-row candidate lists of the
+    sparse path overflow (rows fall back to the cooperative rescan) and the patch list approaches its capacity."""
+    kw = synth.layout_kwargs(layout, pos_iou_threshold=0.02, neg_iou_limit=0.01)
+    enc = enc_mod.SSDInputEncoder(**kw)
+    oenc = orc.SSDInputEncoder(**kw)
+    H, W = kw['img_height'], kw['img_width']
+    gt = [np.array([[1, 0.05 * W, 0.05 * H, 0.95 * W, 0.95 * H], [2, 0.1 * W, 0.2 * H, 0.6 * W, 0.9 * H]], dtype=float),
+          np.array([[3, 0.3 * W, 0.1 * H, 0.9 * W, 0.5 * H]], dtype=float),
+          synth.synth_ground_truth(H, W, kw['n_classes'], 1, 5, max_boxes=9, min_boxes=9)[0]]
+    y, mi = enc(gt, return_matches=True)
+    yo, mo = oenc(gt, return_matches=True)
+    assert np.array_equal(mi, mo)
+    assert (mi >= 0).mean() > 0.5
+    C = kw['n_classes'] + 1
+    assert np.array_equal(y[:, :, :C], yo[:, :, :C]) and np.array_equal(y[:, :, C + 4:], yo[:, :, C + 4:])
+    assert rel_err(y, yo).max() <= OFFSET_RTOL
