@@ -92,11 +92,47 @@ __device__ __forceinline__ SBox<InT> decode_box(const InT* row, int C, const Dec
 // aggregates the per-class counts with ballots, ONE warp-wide atomicAdd reserves the slots of all
 // classes present in the warp (lane c reserves for class c), and the keys are written.  Warps never
 // wait for one another, so there is no block-level synchronisation inside a tile.
+// Deferred key write-out of the image-sweep path (TMA kernel).  A warp collects the composite keys of its tiles
+// in its own shared-memory buffer of two halves.  When a half is full (or the image changes) the warp reserves
+// the slots with ONE global atomicAdd and goes on filling the other half; the keys of a half leave for global
+// memory when the half is needed again - several tiles later, when the atomic's round trip is long over.  So no
+// warp waits for an atomic while it holds a pipeline stage, the atomics per image drop from one per warp-tile
+// to one per D1_PEND_HALF keys, and the keys leave in contiguous runs.  (The CTAs own contiguous tile ranges,
+// so a warp stays inside one image for ~35 tiles.)
+constexpr int D1_PEND_HALF = 32;              // keys per half, two halves per warp
+struct PendingKeys {
+    unsigned long long* buf;       // this warp's 2 x D1_PEND_HALF keys in shared memory
+    int cur;                       // half being filled
+    int n_cur, b_cur;              // its keys and their image
+    int n_pend, b_pend;            // the other half: keys waiting for their write-out, their image
+    int base_pend;                 // lane 31: first reserved slot of the waiting half (result of the atomic)
+};
+__device__ __forceinline__ void retire_pending(PendingKeys& pk, unsigned long long* __restrict__ keys, size_t img_stride) {
+    if (pk.n_pend == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int base = __shfl_sync(0xffffffffu, pk.base_pend, 31);
+    unsigned long long* out = keys + (size_t)pk.b_pend * img_stride + base;
+    const unsigned long long* src = pk.buf + (pk.cur ^ 1) * D1_PEND_HALF;
+    if (lane < pk.n_pend) out[lane] = src[lane];
+    pk.n_pend = 0;
+    __syncwarp();
+}
+// the half being filled becomes the waiting half (its slots are reserved now, written later)
+__device__ __forceinline__ void close_current(PendingKeys& pk, int* __restrict__ seg_count, unsigned long long* __restrict__ keys,
+                                              size_t img_stride) {
+    if (pk.n_cur == 0) return;
+    retire_pending(pk, keys, img_stride);
+    if ((threadIdx.x & 31) == 31) pk.base_pend = atomicAdd(&seg_count[pk.b_cur], pk.n_cur);     // (nobody waits for it now)
+    pk.n_pend = pk.n_cur; pk.b_pend = pk.b_cur;
+    pk.cur ^= 1; pk.n_cur = 0;
+}
+
 template <typename InT, bool FAST>
 __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int rows, int b, int a0,
                                              const DecodeArgs& g, InT thr, int* __restrict__ seg_count,
                                              typename KeyOf<InT>::type* __restrict__ keys,
-                                             SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
+                                             SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class,
+                                             PendingKeys* pk = nullptr) {
     typedef typename KeyOf<InT>::type KeyT;
     const int W = g.W, C = g.C, NS = g.NS, A = g.A;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -155,10 +191,32 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
+            if (pk) {
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(keys);
+                if (total <= D1_PEND_HALF) {
+                    if (pk->n_cur && (pk->b_cur != b || pk->n_cur + total > D1_PEND_HALF)) close_current(*pk, seg_count, gkeys, (size_t)NS * A);
+                    unsigned long long* ck = pk->buf + pk->cur * D1_PEND_HALF + pk->n_cur + (incl - cnt);
+                    for (unsigned mm = mask; mm; mm &= mm - 1) {
+                        const int c = __ffs(mm) - 1;
+                        *ck++ = ((unsigned long long)ord32((float)row[1 + c0 + c]) << 32) |
+                                ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
+                                (unsigned long long)(0xffffffu - (unsigned)a);
+                    }
+                    __syncwarp();
+                    pk->n_cur += total; pk->b_cur = b;
+                    box_done = true;
+                    continue;
+                }
+                // (a dense warp-tile: everything parked goes out first, then the direct path below)
+                close_current(*pk, seg_count, gkeys, (size_t)NS * A);
+                retire_pending(*pk, gkeys, (size_t)NS * A);
+            }
             int base = 0;
             if (lane == 31) base = atomicAdd(&seg_count[b], incl);
-            // the slot reservation is in flight (an L2 round trip): decode this anchor's box meanwhile
-            if (mask && !box_done) { boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g); box_done = true; }
+            // (no box decode here: the sweep decodes the boxes of the candidates it actually visits - a fraction of
+            // those that pass the threshold - from y_pred itself, with all lanes busy)
+            box_done = true;
             base = __shfl_sync(0xffffffffu, base, 31);
             unsigned long long* ck = reinterpret_cast<unsigned long long*>(keys) + (size_t)b * NS * A + base + (incl - cnt);
             for (unsigned mm = mask; mm; mm &= mm - 1) {
@@ -299,14 +357,20 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
     }
     __syncthreads();
 
+    // every CTA owns a contiguous range of tiles (a warp then stays inside one image for many tiles, which is what
+    // lets it batch its slot reservations)
+    const int per = total_tiles / (int)gridDim.x, extra = total_tiles - per * (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+    const int t_end = t_begin + per + ((int)blockIdx.x < extra ? 1 : 0);
     if (warp == D1_THREADS / 32) {
         // ---- producer warp ----
         if (lane == 0) {
+            int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
+                if (tile_id == g.tiles) { tile_id = 0; ++b; }
                 const int s = it % D1_STAGES;
                 if (it >= D1_STAGES) mbar_wait(&empty[s], (uint32_t)(((it / D1_STAGES) - 1) & 1));
-                const int b = t / g.tiles, tile_id = t - b * g.tiles;
                 const int a0 = tile_id * g.tile_rows;
                 const int rows = min(g.tile_rows, A - a0);
                 const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
@@ -317,21 +381,28 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
         return;
     }
     // ---- consumer warps ----
-    // (image / tile of the CTA's next tile by increments: no integer division per tile)
-    const int step_b = (int)gridDim.x / g.tiles, step_t = (int)gridDim.x - step_b * g.tiles;
-    int b = (int)blockIdx.x / g.tiles, tile_id = (int)blockIdx.x - b * g.tiles;
+    PendingKeys pend;
+    pend.buf = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)D1_STAGES * stage_bytes) + (size_t)warp * 2 * D1_PEND_HALF;
+    pend.cur = 0; pend.n_cur = 0; pend.b_cur = 0; pend.n_pend = 0; pend.b_pend = 0; pend.base_pend = 0;
+    const bool defer = (sizeof(InT) == 4) && !FAST && g.sweep;
+    int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, b += step_b, tile_id += step_t) {
-        if (tile_id >= g.tiles) { tile_id -= g.tiles; ++b; }
+    for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
+        if (tile_id == g.tiles) { tile_id = 0; ++b; }
         const int s = it % D1_STAGES;
         mbar_wait(&full[s], (uint32_t)((it / D1_STAGES) & 1));
         const int a0 = tile_id * g.tile_rows;
         const int rows = min(g.tile_rows, A - a0);
-        if (!g.dbg_null)
+        if (g.dbg_null != 1)
             process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
-                                    seg_count, keys, boxes, aux_class);
+                                    seg_count, keys, boxes, aux_class, defer ? &pend : nullptr);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);             // this warp is done with stage s
+    }
+    if (defer) {
+        unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(keys);
+        close_current(pend, seg_count, gkeys, (size_t)g.NS * A);
+        retire_pending(pend, gkeys, (size_t)g.NS * A);
     }
 }
 
@@ -747,7 +818,7 @@ __device__ __forceinline__ unsigned ck_anchor(unsigned long long k) { return 0xf
 template <typename IouT, bool TF, int SW_THREADS>
 __global__ void __launch_bounds__(SW_THREADS)
 sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
-             const SBox<float>* __restrict__ boxes, DecodeArgs g,
+             const float* __restrict__ y, DecodeArgs g,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
     constexpr int SW_WARPS = SW_THREADS / 32;
     __shared__ unsigned long long ck[SW_CHUNK];                  // current chunk, sorted descending
@@ -771,7 +842,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
     const int K = g.K;
     const int n = img_count[b];
     const unsigned long long* gk = keys + (size_t)b * img_stride;
-    const SBox<float>* bx = boxes + (size_t)b * g.A;
+    const float* yb = y + (size_t)b * g.A * g.W;                 // this image's rows of y_pred
     const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
     const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
     const bool screen_ok = thr_ok && g.sx > 0.0 && g.sy > 0.0 && !TF;
@@ -892,7 +963,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         // ------------------------------------------------------------ sweep the chunk
         // all candidate boxes of the chunk are fetched up front (one L2 round trip for the CTA instead
         // of one per step on the critical path)
-        for (int i = tid; i < cn; i += SW_THREADS) cbox[i] = bx[ck_anchor(ck[i])];
+        for (int i = tid; i < cn; i += SW_THREADS) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
         __syncthreads();
         // warp 0 owns the step state: lane <-> candidate.  `stage` publishes a step's candidates
         unsigned long long key = 0;
@@ -1423,8 +1494,8 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
                         (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
     if (tma_ok) {
         const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
-        const size_t smem = stage_bytes * D1_STAGES;
-        int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+        const size_t smem = stage_bytes * D1_STAGES + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF * sizeof(unsigned long long);
+        int ctas_per_sm = (int)((226 * 1024) / (smem + 1024 + 256));
         if (ctas_per_sm > 4) ctas_per_sm = 4;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only)
@@ -1473,11 +1544,11 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
         if (narrow)
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
-                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g,
                 d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         else
             sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, 0, st>>>(
-                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const SBox<float>*>(d->boxes.p), g,
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g,
                 d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         SSDC_TRY(check_launch("sweep_kernel"));
     }
@@ -1662,7 +1733,7 @@ static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* 
     int rows = D1_THREADS;
     while (rows > 32 && ((size_t)rows * g.W + 4) * elem + 4096 > 100 * 1024) rows >>= 1;
     g.tile_rows = rows;
-    g.dbg_null = getenv("SSDC_D1_NULL") != nullptr;
+    g.dbg_null = getenv("SSDC_D1_NULL") ? atoi(getenv("SSDC_D1_NULL")) : 0;
     g.tiles = (int)((job.A + rows - 1) / rows);
     // float32 input stays float32 end to end only where the reference never upcasts:
     // input_coords == 'corners' (ssd_output_decoder.py:186-190) and the Keras layers.
