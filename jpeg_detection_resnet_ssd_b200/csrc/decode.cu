@@ -9,11 +9,13 @@
 // Kernels (one family per numpy stage; details in DESIGN.md section 3):
 //   D1 decode_filter_tma_kernel : stream y_pred (B, A, C+12) once from HBM: warp-specialised persistent
 //                             CTAs, TMA bulk copies of whole-row tiles into a shared-memory ring; per
-//                             (anchor, class) confidence threshold, warp-aggregated compaction, anchor-offset
-//                             decode of every anchor that produced a candidate (decode_filter_kernel: LDG
-//                             fallback for unaligned inputs).
+//                             (anchor, class) confidence threshold, warp-aggregated compaction (image-sweep
+//                             path: keys parked per warp in shared memory, one slot reservation per 32 keys);
+//                             general path: anchor-offset decode of every anchor that produced a candidate
+//                             (decode_filter_kernel: LDG fallback for unaligned inputs).
 //   S  sweep_kernel         : hot configuration (finite top_k): per image radix-select + sort of the best
-//                             candidates and ONE descending class-aware NMS sweep that stops at top_k;
+//                             candidates, anchor-offset decode of their boxes from y_pred, and ONE
+//                             descending class-aware NMS sweep that stops at top_k;
 //                             writes the final rows at (B, top_k, 6) stride.  scan_counts_kernel +
 //                             sweep_pack_kernel pack them for the host copy at collect time.
 //   general path (top_k='all', decode_detections_fast, float64 input, greedy_nms):
