@@ -927,6 +927,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
             }
             tau = prefix;                               // lower edge of the selected bucket
         }
+        if (g.dbg_null == 11) break;                  // (timing experiments: stop after the selection)
         // compact {tau <= key < hi} into shared memory
         if (tid == 0) s_cnt = 0;
         __syncthreads();
@@ -944,6 +945,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         }
         __syncthreads();
         const int cn = (int)s_cnt;
+        if (g.dbg_null == 12) break;                  // (... after the compaction)
         {
             const int N = pow2_ceil(cn > 1 ? cn : 1);
             for (int i = cn + tid; i < N; i += SW_THREADS) ck[i] = 0ull;
@@ -962,11 +964,13 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
             }
         }
 
+        if (g.dbg_null == 13) break;                  // (... after the sort)
         // ------------------------------------------------------------ sweep the chunk
         // all candidate boxes of the chunk are fetched up front (one L2 round trip for the CTA instead
         // of one per step on the critical path)
         for (int i = tid; i < cn; i += SW_THREADS) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
         __syncthreads();
+        if (g.dbg_null == 14) break;                  // (... after the box decode)
         // warp 0 owns the step state: lane <-> candidate.  `stage` publishes a step's candidates
         unsigned long long key = 0;
         bool valid = false;
