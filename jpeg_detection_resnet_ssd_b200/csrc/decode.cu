@@ -807,8 +807,8 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 //            class (lane <-> kept box, raw-corner disjointness), overlapping pairs are decided in
 //            batches (exact, division-free), warp 0 resolves the step and appends to the kept list.
 // ---------------------------------------------------------------------------
-// Threads per CTA (= per image) are a template parameter: 256 when all images fit one wave of 4 CTAs per
-// SM, else 128 (7 CTAs per SM: B = 1024 on 148 SMs is one wave instead of 1.7).
+// Threads per CTA (= per image) are a template parameter: 256 when all images fit one wave of 3 CTAs per
+// SM, else 128 (7 CTAs per SM: B = 1024 on 148 SMs is one wave).
 constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
 constexpr int SW_TARGET = 288;          // the selection aims at >= this many (and <= SW_CHUNK)
 constexpr int SW_KMAX = 256;            // largest top_k the sweep path handles
@@ -946,6 +946,13 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         __syncthreads();
         const int cn = (int)s_cnt;
         if (g.dbg_null == 12) break;                  // (... after the compaction)
+        // the boxes of the chunk are decoded from y_pred after the sort: pull those rows towards L2 now, so that
+        // the DRAM round trip runs under the sort
+        for (int i = tid; i < cn; i += SW_THREADS) {
+            const float* rt = yb + (size_t)ck_anchor(ck[i]) * g.W + g.C;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt + 11));
+        }
         {
             const int N = pow2_ceil(cn > 1 ? cn : 1);
             for (int i = cn + tid; i < N; i += SW_THREADS) ck[i] = 0ull;
@@ -966,9 +973,11 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
 
         if (g.dbg_null == 13) break;                  // (... after the sort)
         // ------------------------------------------------------------ sweep the chunk
-        // all candidate boxes of the chunk are fetched up front (one L2 round trip for the CTA instead
-        // of one per step on the critical path)
-        for (int i = tid; i < cn; i += SW_THREADS) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
+        // The boxes of the chunk are decoded from their y_pred rows two steps ahead of their use: the first 64
+        // here, the rest by warp 1 while warp 0 resolves a step - candidates the sweep never reaches (top_k kept
+        // before the chunk is exhausted) are never decoded, and the float64 `exp` runs in otherwise idle time.
+        const bool lazy = g.dbg_null != 20;
+        for (int i = tid; i < (lazy ? min(cn, 64) : cn); i += SW_THREADS) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
         __syncthreads();
         if (g.dbg_null == 14) break;                  // (... after the box decode)
         // warp 0 owns the step state: lane <-> candidate.  `stage` publishes a step's candidates
@@ -1086,6 +1095,9 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
                 if (lane == 0) s_nkept = nk2;
                 __syncwarp();
                 if (t0 + 32 < cn && nk2 < K) stage(t0 + 32);
+            } else if (warp == 1 && lazy) {
+                const int i = t0 + 64 + lane;           // the step after next
+                if (i < cn) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
             }
             __syncthreads();
         }
@@ -1545,8 +1557,9 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
-        // one image per CTA: 256 threads while every image is resident at once (4 CTAs per SM), else 128 (7 per SM)
-        bool narrow = B > 4LL * d->sm_count;
+        // one image per CTA: 256 threads while every image is resident at once (3 CTAs per SM at 72 registers), else 128
+        // threads (7 per SM)
+        bool narrow = B > 3LL * d->sm_count;
         if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
         if (narrow)
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
