@@ -159,6 +159,17 @@ int ssdc_decode_submit(ssdc_ctx* ctx, const void* y_pred, int dtype, int on_devi
 int ssdc_decode_collect(ssdc_ctx* ctx, double* out_rows, int64_t capacity_rows,
                         int32_t* out_counts, int32_t* out_anchor_idx, int64_t* total_rows);
 
+/* Device-resident results of the submitted decode on `dev_slot`, for consumers that stay on the GPU (no
+ * counterpart in the reference; SURVEY section 7 hard part 5).  Available when the decode ran with a finite
+ * `top_k` on float32 input in per-class or layer mode (the image-sweep path): `*rows` points to
+ * (B_slot, top_k, 6) float64 rows [class, conf, xmin, ymin, xmax, ymax] - the layout of the reference's
+ * `DecodeDetections` layer output, rows beyond an image's count are unspecified -, `*anchors` to (B_slot, top_k)
+ * anchor indices, `*counts` to (B_slot,) row counts; `*b0` / `*n_images` give the image range of the slot's
+ * shard.  The pointers are valid until the next decode on this context; work on them has to be ordered after
+ * the context's stream (`ssdc_synchronize`).  SSDC_ERR_STATE for other configurations (use `ssdc_decode_collect`). */
+int ssdc_decode_results_dev(ssdc_ctx* ctx, int dev_slot, const double** rows, const int32_t** anchors,
+                            const int32_t** counts, int64_t* b0, int64_t* n_images, int32_t* top_k);
+
 /* submit + collect. */
 int ssdc_decode(ssdc_ctx* ctx, const void* y_pred, int dtype, int64_t B, int64_t A, int C,
                 const ssdc_decode_params* p, double* out_rows, int64_t capacity_rows,

@@ -77,6 +77,7 @@ SIGNATURES = {
     'ssdc_decode_submit': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, C.POINTER(DecodeParams)]),
     'ssdc_decode_collect': (_i, [_vp, _vp, _i64, _vp, _vp, _pi64]),
     'ssdc_decode': (_i, [_vp, _vp, _i, _i64, _i64, _i, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _pi64]),
+    'ssdc_decode_results_dev': (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64, _pi64, C.POINTER(C.c_int32)]),
     'ssdc_greedy_nms': (_i, [_vp, _vp, _vp, _i64, _d, _i, _i, _vp, _pi64]),
     'ssdc_encoder_create': (_i, [_vp, _vp, _i64, _vp, C.POINTER(EncodeParams), C.POINTER(_vp)]),
     'ssdc_encoder_destroy': (None, [_vp]),

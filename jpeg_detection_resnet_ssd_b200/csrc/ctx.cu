@@ -319,6 +319,24 @@ int ssdc_decode_collect(ssdc_ctx* ctx, double* out_rows, int64_t capacity_rows,
     return SSDC_OK;
 }
 
+int ssdc_decode_results_dev(ssdc_ctx* ctx, int dev_slot, const double** rows, const int32_t** anchors,
+                            const int32_t** counts, int64_t* b0, int64_t* n_images, int32_t* top_k) {
+    if (!ctx || dev_slot < 0 || dev_slot >= (int)ctx->devs.size()) { set_error("ssdc_decode_results_dev: bad argument"); return SSDC_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevCtx& d = ctx->devs[dev_slot];
+    if (!d.job.valid || !d.job.padded) {
+        set_error("ssdc_decode_results_dev: no device-resident padded result (needs a finite top_k, float32 input, per-class or layer mode)");
+        return SSDC_ERR_STATE;
+    }
+    if (rows) *rows = d.pad_rows.as<double>();
+    if (anchors) *anchors = d.pad_anchor.as<int32_t>();
+    if (counts) *counts = d.out_count.as<int32_t>();
+    if (b0) *b0 = d.job.b0;
+    if (n_images) *n_images = d.job.B;
+    if (top_k) *top_k = d.job.p.top_k;
+    return SSDC_OK;
+}
+
 int ssdc_decode(ssdc_ctx* ctx, const void* y_pred, int dtype, int64_t B, int64_t A, int C,
                 const ssdc_decode_params* p, double* out_rows, int64_t capacity_rows,
                 int32_t* out_counts, int32_t* out_anchor_idx, int64_t* total_rows) {

@@ -80,6 +80,7 @@ struct DecodeJob {
     int C = 0, NS = 0, dtype = 0;
     ssdc_decode_params p;
     bool emitted = false;           // rows already written on the device
+    bool padded = false;            // image-sweep path: (B, top_k, 6) rows + counts are on the device (pad_rows / pad_anchor / out_count)
     bool scan_pending = false;      // image-sweep path: padded rows are on the device, the packed row offsets are not computed yet
     int64_t out_capacity = 0;       // rows the device out buffer can hold
     int iou_f32 = 0;

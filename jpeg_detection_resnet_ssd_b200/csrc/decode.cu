@@ -1804,6 +1804,7 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     SSDC_TRY(r);
 
     job.scan_pending = g.sweep != 0;
+    job.padded = g.sweep != 0;
     if (g.K > 0 && !g.sweep) {
         // bounded output: rows can be emitted right away without knowing the total
         job.out_capacity = B * (int64_t)g.K;

@@ -277,3 +277,47 @@ def test_sub_batching_and_threads(ctx, monkeypatch):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_device_resident_results(ctx):
+    """`ssdc_decode_results_dev`: the (B, top_k, 6) rows + counts the decode step leaves in HBM equal what
+    `ssdc_decode_collect` packs for the host; other configurations report SSDC_ERR_STATE."""
+    import ctypes as C
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    lib = ctx.lib
+    enc = synth.make_encoder(SSDInputEncoder, "ssd300")
+    B, K = 12, 50
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, B, 77, bg_bias=7.0, hot=30)
+    A = y.shape[1]
+    d_y = ctx.dev_alloc(y.nbytes)
+    _lib.check(lib.ssdc_memcpy_h2d(ctx.handle, 0, d_y, _lib.ptr(y), y.nbytes))
+    p = _lib.DecodeParams()
+    p.mode, p.input_coords, p.normalize, p.border_pixels = _lib.MODE_PER_CLASS, 0, 1, 0
+    p.top_k, p.nms_cap, p.log_wh, p.do_nms = K, 0, 1, 1
+    p.conf_thresh, p.iou_thresh, p.img_h, p.img_w = 0.01, 0.45, 300.0, 300.0
+    _lib.check(lib.ssdc_decode_submit(ctx.handle, d_y, _lib.F32, 1, B, A, 21, C.byref(p)))
+    rows_p, anch_p, cnt_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    b0, nimg, topk = C.c_int64(), C.c_int64(), C.c_int32()
+    _lib.check(lib.ssdc_decode_results_dev(ctx.handle, 0, C.byref(rows_p), C.byref(anch_p), C.byref(cnt_p),
+                                           C.byref(b0), C.byref(nimg), C.byref(topk)))
+    assert (b0.value, nimg.value, topk.value) == (0, B, K)
+    ctx.synchronize()
+    pad = np.empty((B, K, 6)); pa = np.empty((B, K), np.int32); cnt = np.empty(B, np.int32)
+    _lib.check(lib.ssdc_memcpy_d2h(ctx.handle, 0, _lib.ptr(pad), rows_p, pad.nbytes))
+    _lib.check(lib.ssdc_memcpy_d2h(ctx.handle, 0, _lib.ptr(pa), anch_p, pa.nbytes))
+    _lib.check(lib.ssdc_memcpy_d2h(ctx.handle, 0, _lib.ptr(cnt), cnt_p, cnt.nbytes))
+    rows = np.empty((B * K, 6)); counts = np.empty(B, np.int32); anchors = np.empty(B * K, np.int32)
+    total = C.c_int64()
+    _lib.check(lib.ssdc_decode_collect(ctx.handle, _lib.ptr(rows), B * K, _lib.ptr(counts), _lib.ptr(anchors), C.byref(total)))
+    assert np.array_equal(cnt, counts) and int(total.value) == int(counts.sum()) and counts.max() == K
+    off = 0
+    for b in range(B):
+        n = int(counts[b])
+        assert np.array_equal(pad[b, :n], rows[off:off + n]) and np.array_equal(pa[b, :n], anchors[off:off + n])
+        off += n
+    # top_k = 'all' has no padded layout
+    p.top_k = 0
+    _lib.check(lib.ssdc_decode_submit(ctx.handle, d_y, _lib.F32, 1, B, A, 21, C.byref(p)))
+    rc = lib.ssdc_decode_results_dev(ctx.handle, 0, C.byref(rows_p), None, None, None, None, None)
+    assert rc == _lib.ERR_STATE
+    ctx.dev_free(d_y)
