@@ -1138,7 +1138,8 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
     int* taken = rb_idx + m;                                               // m   zeroed columns
     int* done = taken + m;                                                 // m
     int* nlist = done + m;                                                 // m   usable list entries (0: none)
-    int* s_goff = nlist + m;                                               // K + 1
+    int* s_match = nlist + m;                                              // m   matches (matching_utils.py:59-77)
+    int* s_goff = s_match + m;                                             // K + 1
     int* s_gcls = s_goff + K + 1;                                          // ngroups
     int* s_list = s_gcls + ngroups;                                        // ngroups
     for (int i = tid; i < ngroups; i += EG_WARPS * 32) { s_gbox[i] = f.grp_box[i]; s_gcls[i] = f.grp_cls[i]; }
@@ -1157,7 +1158,7 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
         if (lane == 0) {
             nlist[r] = usable ? n : 0;
             rb_val[r] = bv; rb_idx[r] = bi; done[r] = 0;
-            match[g0 + r] = 0;             // matches = np.zeros(num_ground_truth_boxes) (matching_utils.py:59)
+            s_match[r] = 0;                // matches = np.zeros(num_ground_truth_boxes) (matching_utils.py:59)
             if (bi == 0x7fffffff) { atomicOr(&s_rescan[r >> 5], 1u << (r & 31)); s_more = 1; }
         }
     }
@@ -1292,11 +1293,22 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
                     const double v = rb_val[r];
                     if (better(v, r, bv, bg)) { bv = v; bg = r; }
                 }
-                warp_best(bv, bg);
+                if (irrb) warp_best(bv, bg);
+                else {
+                    // regular input: the values are >= +0, so their bit patterns order like unsigned integers -
+                    // three REDUX instead of five shuffle rounds (first row on ties: np.argmax)
+                    const bool has = bg != 0x7fffffff;
+                    const unsigned long long bits = has ? (unsigned long long)__double_as_longlong(bv) : 0ull;
+                    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+                    const unsigned mh = __reduce_max_sync(0xffffffffu, has ? hi : 0u);
+                    const bool top = has && hi == mh;
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, top ? lo : 0u);
+                    bg = (int)__reduce_min_sync(0xffffffffu, (top && lo == ml) ? (unsigned)bg : 0x7fffffffu);
+                }
                 const int asel = rb_idx[bg];
                 __syncwarp();
                 if (lane == 0) {
-                    match[g0 + bg] = asel;
+                    s_match[bg] = asel;
                     rb_val[bg] = 0.0;            // weight_matrix[ground_truth_index] = 0 -> argmax 0, weight 0
                     rb_idx[bg] = 0;
                     done[bg] = 1;
@@ -1307,6 +1319,7 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
                 // rows whose best column was just zeroed need a new maximum (every open row for irregular inputs)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    if (32 * j >= m) { if (lane == 0) s_rescan[j] = 0; continue; }
                     const int rr = 32 * j + lane;
                     const bool again = (rr < m) && !done[rr] && (irrb || rb_idx[rr] == asel);
                     unsigned mk = __ballot_sync(0xffffffffu, again);
@@ -1330,16 +1343,20 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
         __syncthreads();
         if (!s_more) break;
     }
-    if (tid == 0) {
-        const int basep = plist ? atomicAdd(pcount, m) : 0;
-        for (int r = 0; r < m; ++r) {
-            const long long pos = (long long)b * g.A + match[g0 + r];
-            cand[pos] = r;
-            if (plist) plist[basep + r] = (int)pos;
-        }
+    // y_encoded[i, bipartite_matches, :-8] = labels_one_hot in row order: the LAST row that names an anchor wins
+    __shared__ int s_base;
+    if (tid == 0) s_base = plist ? atomicAdd(pcount, m) : 0;
+    __syncthreads();
+    for (int r = tid; r < m; r += EG_WARPS * 32) {
+        const int a = s_match[r];
+        bool last = true;
+        for (int r2 = r + 1; r2 < m; ++r2) last = last && (s_match[r2] != a);
+        const long long pos = (long long)b * g.A + a;
+        if (last) cand[pos] = r;
+        if (plist) plist[s_base + r] = (int)pos;
+        match[g0 + r] = a;
     }
 }
-
 
 // E3 patch of the sparse path: rows whose `cand` entry is not -1 differ from the template
 __device__ __forceinline__ void apply_one(int c, long long i, const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
@@ -1654,7 +1671,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             }
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_MATCH);
-                const size_t smem = (size_t)(ngroups + f.K) * sizeof(float4) + (size_t)max_m * (sizeof(double) + 4 * sizeof(int)) + (f.K + 1 + 2 * (size_t)ngroups) * sizeof(int) + 16;
+                const size_t smem = (size_t)(ngroups + f.K) * sizeof(float4) + (size_t)max_m * (sizeof(double) + 5 * sizeof(int)) + (f.K + 1 + 2 * (size_t)ngroups) * sizeof(int) + 16;
                 SSDC_CUDA(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 greedy_kernel<<<(unsigned)B, EG_WARPS * 32, smem, st>>>(gtp, gt_off, f, g, gtau, lcnt, lval, lidx, img_irr, cand, match, plist, pcount);
                 SSDC_TRY(check_launch("greedy_kernel"));
