@@ -1557,9 +1557,10 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
-        // one image per CTA: 256 threads while every image is resident at once (3 CTAs per SM at 72 registers), else 128
-        // threads (7 per SM)
-        bool narrow = B > 3LL * d->sm_count;
+        // one image per CTA: 128 threads (7 CTAs per SM) for large batches, 256 threads (3 per SM) otherwise.  Between 3
+        // and 4 images per SM the narrow variant is faster on sparse inputs (one wave instead of two) but much slower on
+        // dense ones (too few warps per SM: SSD512 at conf 0.001, B = 512: 2.0 vs 1.15 ms) - the density is not known here.
+        bool narrow = B > 4LL * d->sm_count;
         if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
         if (narrow)
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
