@@ -245,6 +245,16 @@ int ssdc_match_bipartite_greedy(ssdc_ctx* ctx, const double* weights, int64_t m,
 int ssdc_match_multi(ssdc_ctx* ctx, const double* weights, int64_t m, int64_t n, double threshold,
                      int64_t* out_gt, int64_t* out_anchor, int64_t* n_matches);
 
+/* SSDLoss.compute_loss   keras_loss_function/keras_ssd_loss.py:98-211 (log_loss :78-96, smooth_L1_loss :53-76),
+ * forward pass.  `y_true` (B, A, C+12) float32 or float64 (`dtype_true`; converted to float32 like the Keras
+ * placeholder), `y_pred` (B, A, C+12) float32; both host pointers, or both device pointers on dev_slot 0 when
+ * `on_device != 0` (e.g. the device-resident output of `ssdc_encode`).  Writes the per-image loss (B,) float32 to
+ * the host array `out_loss`.  Hard negative mining as in the reference: the `min(max(neg_pos_ratio * n_positive,
+ * n_neg_min), #non-zero negative losses)` largest negative classification losses of the whole batch are kept,
+ * equal values in flat index order (tf.nn.top_k). */
+int ssdc_ssd_loss(ssdc_ctx* ctx, const void* y_true, int dtype_true, const float* y_pred, int on_device,
+                  int64_t B, int64_t A, int C, int neg_pos_ratio, int n_neg_min, double alpha, float* out_loss);
+
 /* ---- evaluation --------------------------------------------
  * Evaluator.match_predictions  eval_utils/average_precision_evaluator.py:570-777.
  * Predictions of all classes back to back: class c (1..n_classes) owns

@@ -89,6 +89,7 @@ SIGNATURES = {
     'ssdc_convert_coordinates': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     'ssdc_match_bipartite_greedy': (_i, [_vp, _vp, _i64, _i64, _vp]),
     'ssdc_match_multi': (_i, [_vp, _vp, _i64, _i64, _d, _vp, _vp, _pi64]),
+    'ssdc_ssd_loss': (_i, [_vp, _vp, _i, _vp, _i, _i64, _i64, _i, _i, _i, _d, _vp]),
     'ssdc_voc_match': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -150,3 +150,23 @@ def test_voc_oracle_matches_golden(case):
         assert np.array_equal(tp[c], g['tp_%d' % c]) and np.array_equal(fp[c], g['fp_%d' % c])
     assert np.array_equal(np.asarray(ap_s, dtype=float), g['ap_sample'])
     assert np.array_equal(np.asarray(ap_i, dtype=float), g['ap_integrate'])
+
+
+def test_ssd_loss_oracle_hand_case():
+    """The loss restatement on a case small enough to evaluate by hand (parity with TensorFlow itself is unpinned)."""
+    from oracle import ssd_loss_oracle as lo
+    C = 3
+    W = C + 12
+    yt = np.zeros((1, 4, W), np.float32)
+    yp = np.zeros((1, 4, W), np.float32)
+    yt[0, 0, 1] = 1
+    yt[0, 1:, 0] = 1
+    yp[0, :, :C] = [[.2, .7, .1], [.9, .05, .05], [.5, .25, .25], [.6, .2, .2]]
+    yt[0, 0, C:C + 4] = [.1, .2, .3, .4]
+    yp[0, 0, C:C + 4] = [0, 0, 0, 2.]
+    # one positive -> the 3 highest negative losses (all three negatives) enter
+    want = -np.log(.7) - np.log(.5) - np.log(.6) - np.log(.9) + 0.5 * (.01 + .04 + .09) + (1.6 - 0.5)
+    assert abs(float(lo.compute_loss(yt, yp)[0]) - want) < 1e-5
+    # ratio 1: only the largest negative loss (-log 0.5)
+    want1 = -np.log(.7) - np.log(.5) + 0.5 * (.01 + .04 + .09) + (1.6 - 0.5)
+    assert abs(float(lo.compute_loss(yt, yp, neg_pos_ratio=1)[0]) - want1) < 1e-5
