@@ -484,12 +484,53 @@ def extra_numbers(ctx, _lib, enc, peak):
         'kernel_ms': {k: round(v[0] / 3, 4) for k, v in prof.items() if v[1]}}
     ctx.dev_free(d_y)
 
+    # SSD loss on the device-resident y_encoded (float64) + a float32 prediction
+    try:
+        out['ssd_loss_b1024'] = loss_numbers(ctx, _lib, enc, peak)
+    except Exception as exc:
+        out['ssd_loss_b1024'] = {'error': repr(exc)[:200]}
+
     # the VOC matching core of the Evaluator (the consumer of the decoder's output)
     try:
         out['voc_match_predictions'] = voc_numbers(ctx)
     except Exception as exc:      # secondary number: never take the headline down
         out['voc_match_predictions'] = {'error': repr(exc)[:200]}
     return out
+
+
+def loss_numbers(ctx, _lib, enc, peak):
+    """`ssdc_ssd_loss` with both tensors resident on the device: y_true = the encoder's float64 output,
+    y_pred = synthetic float32 predictions (64 unique images tiled)."""
+    from jpeg_detection_resnet_ssd_b200 import synth
+    lib = ctx.lib
+    B, A, W = 1024, A_SSD300, 33
+    ctx2, h = enc._encoder()
+    gt = synth.synth_ground_truth(300, 300, 20, B, seed=79)
+    flat, offs = synth.flatten_ground_truth(gt)
+    d_true = ctx.dev_alloc(B * A * W * 8)
+    _lib.check(lib.ssdc_encode(h, _lib.ptr(flat), _lib.ptr(offs), B, 1, d_true, None, None))
+    uniq = 64
+    base = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, N_CLASSES, uniq, 99, bg_bias=3.0, hot=40)
+    d_pred = ctx.dev_alloc(B * A * W * 4)
+    for i in range(0, B, uniq):
+        _lib.check(lib.ssdc_memcpy_h2d(ctx.handle, 0, _lib.C.c_void_p(d_pred.value + i * A * W * 4), _lib.ptr(base), base.nbytes))
+    out = np.empty(B, np.float32)
+
+    def step():
+        _lib.check(lib.ssdc_ssd_loss(ctx.handle, d_true, _lib.F64, d_pred, 1, B, A, N_CLASSES, 3, 0, 1.0, _lib.ptr(out)))
+    for _ in range(3):
+        step()
+    steps = 10
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps          # (the call returns the per-image losses to the host: wall clock)
+    nbytes = B * A * W * 12
+    ctx.dev_free(d_true)
+    ctx.dev_free(d_pred)
+    return {'images_per_s': B / dt, 'ms_per_step': dt * 1e3, 'read_GBps': nbytes / dt / 1e9, 'frac_of_hbm_peak': nbytes / dt / 1e9 / peak,
+            'mean_loss': float(out.mean()), 'note': 'wall clock of ssdc_ssd_loss (device-resident float64 y_true + float32 y_pred, 3.46 MB/image read; '
+                                                    'one host round trip for the mining count, (B,) floats copied back)'}
 
 
 def voc_numbers(ctx):

@@ -35,6 +35,17 @@ struct LossState {
     unsigned hist[256];
 };
 
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldg_stream_d2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 template <typename TrueT>
 __global__ void __launch_bounds__(LS_ROWS)
 loss_box_kernel(const TrueT* __restrict__ y_true, const float* __restrict__ y_pred, long long n_boxes, int A, int C, int W,
@@ -54,9 +65,33 @@ loss_box_kernel(const TrueT* __restrict__ y_true, const float* __restrict__ y_pr
         const int rows = (int)min((long long)LS_ROWS, n_boxes - r0);
         const int n = rows * W;
         __syncthreads();
-        for (int e = tid; e < n; e += LS_ROWS) {
-            sp[e] = y_pred[r0 * W + e];
-            stt[e] = (float)y_true[r0 * W + e];
+        {
+            // (a tile starts at a multiple of LS_ROWS rows: 16-byte aligned for any W when the tensors are)
+            const float* gp = y_pred + r0 * W;
+            const TrueT* gt = y_true + r0 * W;
+            const bool al = ((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(gt)) & 15) == 0;
+            int done_p = 0, done_t = 0;
+            if (al) {
+                const int nv = n >> 2;
+                const float4* g4 = reinterpret_cast<const float4*>(gp);
+                for (int v = tid; v < nv; v += LS_ROWS) reinterpret_cast<float4*>(sp)[v] = ldg_stream_f4(g4 + v);
+                done_p = nv << 2;
+                if (sizeof(TrueT) == 4) {
+                    const float4* t4 = reinterpret_cast<const float4*>(gt);
+                    for (int v = tid; v < nv; v += LS_ROWS) reinterpret_cast<float4*>(stt)[v] = ldg_stream_f4(t4 + v);
+                    done_t = nv << 2;
+                } else {
+                    const int nd = n >> 1;
+                    const double2* t2 = reinterpret_cast<const double2*>(gt);
+                    for (int v = tid; v < nd; v += LS_ROWS) {
+                        const double2 t = ldg_stream_d2(t2 + v);
+                        reinterpret_cast<float2*>(stt)[v] = make_float2((float)t.x, (float)t.y);
+                    }
+                    done_t = nd << 1;
+                }
+            }
+            for (int e = done_p + tid; e < n; e += LS_ROWS) sp[e] = gp[e];
+            for (int e = done_t + tid; e < n; e += LS_ROWS) stt[e] = (float)gt[e];
         }
         __syncthreads();
         float cl = 0.f, ll = 0.f, pos = 0.f, neg = 0.f;
@@ -125,20 +160,36 @@ loss_hist_kernel(const float* __restrict__ nl, long long n, int shift, LossState
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
 }
 
-// the bucket that holds the k-th largest key: buckets are walked from the top
-__global__ void loss_pick_kernel(int shift, LossState* __restrict__ st) {
-    if (threadIdx.x != 0) return;
-    long long k = st->k_rem;
-    int sel = 0;
-    for (int bkt = 255; bkt >= 0; --bkt) {
-        const long long c = st->hist[bkt];
-        if (k <= c) { sel = bkt; break; }
-        k -= c;
+// the bucket that holds the k-th largest key: one warp walks the buckets from the top, lane l owns buckets [8l, 8l+8)
+__global__ void __launch_bounds__(32) loss_pick_kernel(int shift, LossState* __restrict__ st) {
+    const int lane = threadIdx.x;
+    long long h[8];
+    long long mine = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { h[q] = st->hist[lane * 8 + q]; mine += h[q]; }
+    long long suffix = mine;                                  // sum over lanes >= this lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += v;
     }
-    st->prefix |= (unsigned)sel << shift;
-    st->pmask |= 0xffu << shift;
-    st->k_rem = k;
-    for (int bkt = 0; bkt < 256; ++bkt) st->hist[bkt] = 0;
+    const long long k = st->k_rem;
+    const long long above = suffix - mine;                    // keys in higher buckets than this lane's
+    const bool has = above < k && k <= above + mine;
+    __syncwarp();
+    if (has) {
+        long long cum = above;
+        int sel = lane * 8;
+        for (int q = 7; q >= 0; --q) {
+            if (k <= cum + h[q]) { sel = lane * 8 + q; break; }
+            cum += h[q];
+        }
+        st->prefix |= (unsigned)sel << shift;
+        st->pmask |= 0xffu << shift;
+        st->k_rem = k - cum;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st->hist[lane * 8 + q] = 0;
 }
 
 // boxes per image whose negative loss equals the k-th largest value
@@ -159,20 +210,45 @@ loss_eqcount_kernel(const float* __restrict__ nl, int A, const LossState* __rest
 }
 
 // how many of an image's tied boxes are admitted: ties are taken in flat index order (tf.nn.top_k)
-__global__ void loss_quota_kernel(const int* __restrict__ eq, int B, const LossState* __restrict__ st, int* __restrict__ quota) {
-    if (threadIdx.x != 0) return;
-    long long left = st->k_rem;
-    for (int b = 0; b < B; ++b) {
-        const long long q = left < (long long)eq[b] ? left : (long long)eq[b];
-        quota[b] = (int)(q > 0 ? q : 0);
-        left -= q > 0 ? q : 0;
+__global__ void __launch_bounds__(1024)
+loss_quota_kernel(const int* __restrict__ eq, int B, const LossState* __restrict__ st, int* __restrict__ quota) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long need = st->k_rem;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        const long long c = (b < B) ? eq[b] : 0;
+        long long x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += v; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? wsum[warp - 1] : 0) + (x - c);     // ties in earlier images
+        if (b < B) {
+            long long q = need - before;
+            q = q < 0 ? 0 : (q > c ? c : q);
+            quota[b] = (int)q;
+        }
+        __syncthreads();
+        if (tid == 1023) carry = before + c;
+        __syncthreads();
     }
 }
 
 // sum of the classification losses of the kept negatives of one image (:186-189)
 __global__ void __launch_bounds__(256)
 loss_negsum_kernel(const float* __restrict__ nl, const float* __restrict__ closs, int A, const LossState* __restrict__ st,
-                   const int* __restrict__ quota, double* __restrict__ img_neg) {
+                   const int* __restrict__ eq, const int* __restrict__ quota, double* __restrict__ img_neg) {
     __shared__ int wcnt[8];
     __shared__ double wsum[8];
     __shared__ int s_base;
@@ -184,6 +260,10 @@ loss_negsum_kernel(const float* __restrict__ nl, const float* __restrict__ closs
     if (tid == 0) s_base = 0;
     __syncthreads();
     double sum = 0.0;
+    if (eq[blockIdx.x] == q) {
+        // every tie of this image is admitted (or there is none): no ranks needed
+        for (int a = tid; a < A; a += 256) if (ord32(p[a]) >= tau) sum += (double)cl[a];
+    } else
     for (int a0 = 0; a0 < A; a0 += 256) {
         const int a = a0 + tid;
         const unsigned k = (a < A) ? ord32(p[a]) : 0u;
@@ -302,9 +382,9 @@ extern "C" int ssdc_ssd_loss(ssdc_ctx* ctx, const void* y_true, int dtype_true, 
         LaunchScope ls(ctx, &d, SSDC_K_THIN);
         loss_eqcount_kernel<<<(unsigned)B, 256, 0, st>>>(nl, (int)A, stt, eq);
         SSDC_TRY(check_launch("loss_eqcount_kernel"));
-        loss_quota_kernel<<<1, 32, 0, st>>>(eq, (int)B, stt, quota);
+        loss_quota_kernel<<<1, 1024, 0, st>>>(eq, (int)B, stt, quota);
         SSDC_TRY(check_launch("loss_quota_kernel"));
-        loss_negsum_kernel<<<(unsigned)B, 256, 0, st>>>(nl, closs, (int)A, stt, quota, img_neg);
+        loss_negsum_kernel<<<(unsigned)B, 256, 0, st>>>(nl, closs, (int)A, stt, eq, quota, img_neg);
         SSDC_TRY(check_launch("loss_negsum_kernel"));
         ctx->launches.fetch_add(2, std::memory_order_relaxed);
     }
