@@ -1,10 +1,11 @@
 """The SSD multibox loss of the reference (`keras_loss_function/keras_ssd_loss.py`), forward pass, as a
 numpy-in / numpy-out callable on the device.
 
-In the reference `SSDLoss.compute_loss` builds a TensorFlow graph (it is handed to `model.compile`); this class
-keeps the constructor and the method name and evaluates the same arithmetic (`ssdc_ssd_loss`, csrc/loss.cu) for
-monitoring / validation: `compute_loss(y_true, y_pred) -> (batch_size,) float32`.  It is not a Keras loss object
-(no gradients).  `y_true` is what `SSDInputEncoder` returns (float64 or float32), `y_pred` the float32 model
+In the reference `SSDLoss.compute_loss` builds a TensorFlow graph (it is handed to `model.compile`);
+`DeviceSSDLoss` keeps the constructor and the method name and evaluates the same arithmetic (`ssdc_ssd_loss`,
+csrc/loss.cu) for monitoring / validation: `compute_loss(y_true, y_pred) -> (batch_size,) float32`.  It is not a Keras
+loss object (no gradients).  `SSDLoss` is the reference's own class whenever that can be imported (drop-in mode with
+TensorFlow present), else `DeviceSSDLoss`.  `y_true` is what `SSDInputEncoder` returns (float64 or float32), `y_pred` the float32 model
 output of the same shape.  Parity is unpinned (TensorFlow cannot be executed here): the device code and the
 numpy oracle follow the TensorFlow graph op by op in float32.
 """
@@ -13,12 +14,13 @@ from __future__ import division
 import numpy as np
 
 try:
-    from .. import _lib
+    from .. import _lib, _dropin
 except ImportError:
     import _lib
+    import _dropin
 
 
-class SSDLoss:
+class DeviceSSDLoss:
     def __init__(self, neg_pos_ratio=3, n_neg_min=0, alpha=1.0):
         """reference :26-51."""
         self.neg_pos_ratio = neg_pos_ratio
@@ -43,3 +45,11 @@ class SSDLoss:
                                             _lib.ptr(y_pred), 0, B, A, W - 12, int(self.neg_pos_ratio), int(self.n_neg_min),
                                             float(self.alpha), _lib.ptr(out)))
         return out
+
+
+# Drop-in mode: `from keras_loss_function.keras_ssd_loss import SSDLoss` in the reference's training scripts must keep
+# returning the TensorFlow loss that `model.compile` needs.  If the reference's module is importable further down the
+# package path, its class is re-exported unchanged (the device forward pass stays available as `DeviceSSDLoss`);
+# otherwise `SSDLoss` is the device version.
+_ref = _dropin.load_shadowed(__package__ or 'keras_loss_function', 'keras_ssd_loss') if (__package__ or '').split('.')[0] == 'keras_loss_function' else None
+SSDLoss = _ref.SSDLoss if _ref is not None and hasattr(_ref, 'SSDLoss') else DeviceSSDLoss

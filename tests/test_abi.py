@@ -166,3 +166,38 @@ def test_drop_in_keeps_unreplaced_reference_modules(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'), str(fake)]))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
     assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
+
+
+def test_drop_in_extends_partially_replaced_reference_classes(tmp_path):
+    """`eval_utils.average_precision_evaluator` and `keras_loss_function.keras_ssd_loss` replace only a part of the
+    reference modules: with the reference importable, `Evaluator` must be the reference's class with the device
+    matching core, and `SSDLoss` the reference's own (TensorFlow) loss."""
+    import sys
+    fake = tmp_path / 'localisation_part'
+    (fake / 'eval_utils').mkdir(parents=True)
+    (fake / 'eval_utils' / '__init__.py').write_text('')
+    (fake / 'eval_utils' / 'average_precision_evaluator.py').write_text(
+        "class Evaluator(object):\n"
+        "    def __init__(self, *a, **k):\n        self.origin = 'reference'\n"
+        "    def predict_on_dataset(self):\n        return 'reference predict'\n"
+        "    def match_predictions(self):\n        return 'reference match'\n")
+    (fake / 'keras_loss_function').mkdir()
+    (fake / 'keras_loss_function' / '__init__.py').write_text('')
+    (fake / 'keras_loss_function' / 'keras_ssd_loss.py').write_text("class SSDLoss:\n    origin = 'reference'\n")
+    code = (
+        "from eval_utils.average_precision_evaluator import Evaluator, DeviceEvaluator\n"
+        "e = Evaluator()\n"
+        "assert e.origin == 'reference' and e.predict_on_dataset() == 'reference predict'\n"
+        "assert Evaluator.match_predictions is DeviceEvaluator.match_predictions\n"
+        "from keras_loss_function.keras_ssd_loss import SSDLoss, DeviceSSDLoss\n"
+        "assert SSDLoss.origin == 'reference' and hasattr(DeviceSSDLoss, 'compute_loss')\n"
+        "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'), str(fake)]))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
+    assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
+    # stand-alone (no reference on the path): the device classes
+    code2 = ("from jpeg_detection_resnet_ssd_b200.eval_utils.average_precision_evaluator import Evaluator, DeviceEvaluator\n"
+             "from jpeg_detection_resnet_ssd_b200.keras_loss_function.keras_ssd_loss import SSDLoss, DeviceSSDLoss\n"
+             "assert Evaluator is DeviceEvaluator and SSDLoss is DeviceSSDLoss\nprint('ok')\n")
+    r = subprocess.run([sys.executable, '-c', code2], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
