@@ -818,7 +818,7 @@ __device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu
 __device__ __forceinline__ unsigned ck_anchor(unsigned long long k) { return 0xffffffu - (unsigned)(k & 0xffffffu); }
 
 template <typename IouT, bool TF, int SW_THREADS>
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, SW_THREADS == 256 ? 4 : 7)
 sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
              const float* __restrict__ y, DecodeArgs g,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
@@ -1557,9 +1557,9 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
-        // one image per CTA: 128 threads (7 CTAs per SM) for large batches, 256 threads (3 per SM) otherwise.  Between 3
-        // and 4 images per SM the narrow variant is faster on sparse inputs (one wave instead of two) but much slower on
-        // dense ones (too few warps per SM: SSD512 at conf 0.001, B = 512: 2.0 vs 1.15 ms) - the density is not known here.
+        // one image per CTA: 256 threads while every image is resident at once (4 CTAs per SM), else 128 threads (7 per
+        // SM: B = 1024 on 148 SMs is one wave).  (On dense inputs the wide variant is much faster per image: SSD512 at
+        // conf 0.001, B = 512: 1.15 vs 2.0 ms.)
         bool narrow = B > 4LL * d->sm_count;
         if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
         if (narrow)
