@@ -879,7 +879,7 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
     // sorting 512 (K = 200: 0.062 -> 0.054 ms).  Later chunks (heavy suppression): SW_TARGET .. SW_CHUNK.
     int target = K + max(K >> 3, 8), cap = 64;
     while (cap < SW_CHUNK && target + 16 > cap) cap <<= 1;
-    if (target + 16 > cap) { target = SW_TARGET; cap = SW_CHUNK; }
+    if (target + 16 > cap || n > 8 * SW_CHUNK) { target = SW_TARGET; cap = SW_CHUNK; }      // (many candidates: another selection round would cost more than the bigger sort)
     if (target < SW_TARGET / 8) target = SW_TARGET / 8;
     while (true) {
         // ------------------------------------------------------------ select the next chunk
