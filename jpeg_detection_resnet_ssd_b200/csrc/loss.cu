@@ -10,7 +10,8 @@
 // once.  `tf.nn.top_k` takes the lower index first among equal values; so does the selection below.
 //
 // Kernels:
-//   loss_box_kernel      : streams y_true / y_pred once (coalesced tile copies into shared memory, thread = box):
+//   loss_box_tma_kernel  : streams y_true / y_pred once (warp-specialised TMA ring as in D1; loss_box_kernel: plain tile
+//                          copies for unaligned inputs), thread = box:
 //                          log loss, smooth L1, positive / negative masks; per-image partial sums, batch counters,
 //                          per-box classification loss and negative loss for the mining step
 //   loss_hist_kernel +   : 4 x 8-bit radix selection of the k-th largest negative loss over the whole batch
@@ -44,6 +45,56 @@ __device__ __forceinline__ double2 ldg_stream_d2(const double2* p) {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
+}
+
+// One tile of `rows` boxes staged in shared memory (row stride W): thread t evaluates box r0 + t.
+template <typename TrueS>
+__device__ __forceinline__ void loss_rows(const float* __restrict__ sp, const TrueS* __restrict__ stt, int tid, int rows, long long r0,
+                                          long long n_boxes, int A, int C, int W, float* __restrict__ closs, float* __restrict__ nl,
+                                          double* __restrict__ img_pos, double* __restrict__ img_loc, double& my_pos, unsigned long long& my_nz) {
+    const int lane = tid & 31, warp = tid >> 5;
+    float cl = 0.f, ll = 0.f, pos = 0.f, neg = 0.f;
+    const long long i = r0 + tid;
+    if (tid < rows) {
+        const float* yp = sp + (size_t)tid * W;
+        const TrueS* yt = stt + (size_t)tid * W;
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {                                                  // :93-95
+            // 0 * log(finite) adds an exact zero: the logarithm is only evaluated where it can matter (one class
+            // of a one-hot target; a NaN / inf prediction still has to poison the sum like it does in TensorFlow)
+            const float t = (float)yt[c], x = yp[c];
+            if (t != 0.0f || !(fabsf(x) < INFINITY)) acc += t * logf(fmaxf(x, 1e-15f));
+        }
+        cl = -acc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                                  // :72-75
+            const float dlt = (float)yt[C + k] - yp[C + k];
+            const float ab = fabsf(dlt);
+            ll += (ab < 1.0f) ? (0.5f * (dlt * dlt)) : (ab - 0.5f);
+        }
+        neg = (float)yt[0];                                                            // :137
+        pos = (C >= 2) ? (float)yt[1] : -INFINITY;
+        for (int c = 2; c < C; ++c) pos = fmaxf(pos, (float)yt[c]);                    // :138
+        const float nlv = cl * neg;                                                    // :149
+        closs[i] = cl;
+        nl[i] = nlv;
+        my_pos += (double)pos;
+        my_nz += (nlv != 0.0f) ? 1ull : 0ull;
+    }
+    // per-image sums: a warp's 32 boxes belong to one image except at an image boundary
+    const long long b_first = __shfl_sync(0xffffffffu, i / A, 0);
+    const long long i_last = min(r0 + warp * 32 + 31, n_boxes - 1);
+    const bool one_image = (i_last / A) == b_first;
+    const double pc = (tid < rows) ? (double)(cl * pos) : 0.0;                         // :147
+    const double lc = (tid < rows) ? (double)(ll * pos) : 0.0;                         // :197
+    if (one_image) {
+        double a = pc, c2 = lc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o); }
+        if (lane == 0 && r0 + warp * 32 < n_boxes) { atomicAdd(&img_pos[b_first], a); atomicAdd(&img_loc[b_first], c2); }
+    } else if (tid < rows) {
+        atomicAdd(&img_pos[i / A], pc); atomicAdd(&img_loc[i / A], lc);
+    }
 }
 
 template <typename TrueT>
@@ -94,49 +145,113 @@ loss_box_kernel(const TrueT* __restrict__ y_true, const float* __restrict__ y_pr
             for (int e = done_t + tid; e < n; e += LS_ROWS) stt[e] = (float)gt[e];
         }
         __syncthreads();
-        float cl = 0.f, ll = 0.f, pos = 0.f, neg = 0.f;
-        const long long i = r0 + tid;
-        if (tid < rows) {
-            const float* yp = sp + (size_t)tid * W;
-            const float* yt = stt + (size_t)tid * W;
-            float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc += yt[c] * logf(fmaxf(yp[c], 1e-15f));          // :93-95
-            cl = -acc;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                                                  // :72-75
-                const float dlt = yt[C + k] - yp[C + k];
-                const float ab = fabsf(dlt);
-                ll += (ab < 1.0f) ? (0.5f * (dlt * dlt)) : (ab - 0.5f);
-            }
-            neg = yt[0];                                                                   // :137
-            pos = yt[1];
-            for (int c = 2; c < C; ++c) pos = fmaxf(pos, yt[c]);                           // :138
-            if (C < 2) pos = -INFINITY;
-            const float nlv = cl * neg;                                                    // :149
-            closs[i] = cl;
-            nl[i] = nlv;
-            my_pos += (double)pos;
-            my_nz += (nlv != 0.0f) ? 1ull : 0ull;
-        }
-        // per-image sums: a warp's 32 boxes belong to one image except at an image boundary
-        const long long b_first = __shfl_sync(0xffffffffu, i / A, 0);
-        const long long i_last = min(r0 + warp * 32 + 31, n_boxes - 1);
-        const bool one_image = (i_last / A) == b_first;
-        const double pc = (tid < rows) ? (double)(cl * pos) : 0.0;                         // :147
-        const double lc = (tid < rows) ? (double)(ll * pos) : 0.0;                         // :197
-        if (one_image) {
-            double a = pc, c2 = lc;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o); }
-            if (lane == 0 && r0 + warp * 32 < n_boxes) { atomicAdd(&img_pos[b_first], a); atomicAdd(&img_loc[b_first], c2); }
-        } else if (tid < rows) {
-            atomicAdd(&img_pos[i / A], pc); atomicAdd(&img_loc[i / A], lc);
-        }
+        loss_rows<float>(sp, stt, tid, rows, r0, n_boxes, A, C, W, closs, nl, img_pos, img_loc, my_pos, my_nz);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { my_pos += __shfl_xor_sync(0xffffffffu, my_pos, o); my_nz += __shfl_xor_sync(0xffffffffu, my_nz, o); }
     if (lane == 0) { red_pos[warp] = my_pos; red_nz[warp] = my_nz; }
     __syncthreads();
+    if (tid == 0) {
+        double p = 0.0; unsigned long long z = 0;
+        for (int w = 0; w < LS_ROWS / 32; ++w) { p += red_pos[w]; z += red_nz[w]; }
+        atomicAdd(&st->n_pos, p);
+        atomicAdd(&st->n_nonzero, z);
+    }
+}
+
+// ---- TMA variant of the box kernel: warp-specialised persistent CTAs, exactly the structure of D1
+// (decode.cu): one producer warp keeps a 2-stage ring of tiles - LS_ROWS rows of y_pred and of y_true each, in
+// their own dtypes - filled with cp.async.bulk + full / empty mbarriers; four consumer warps evaluate a tile as
+// soon as it has landed.  Every CTA owns a contiguous range of tiles.  Needs 16-byte aligned tensors and
+// n_boxes % 4 == 0 (else loss_box_kernel above).
+__device__ __forceinline__ uint32_t ls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ls_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ls_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ls_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ls_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ls_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LS_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra LS_WAIT_DONE;\n"
+        "bra LS_WAIT_LOOP;\n"
+        "LS_WAIT_DONE:\n"
+        "}\n" :: "r"(ls_smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void ls_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ls_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ls_tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(ls_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ls_smem_u32(bar)) : "memory");
+}
+
+constexpr int LS_STAGES = 2;
+template <typename TrueT>
+__global__ void __launch_bounds__(LS_ROWS + 32)
+loss_box_tma_kernel(const TrueT* __restrict__ y_true, const float* __restrict__ y_pred, long long n_boxes, int A, int C, int W,
+                    float* __restrict__ closs, float* __restrict__ nl, double* __restrict__ img_pos, double* __restrict__ img_loc,
+                    LossState* __restrict__ st) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[LS_STAGES];
+    __shared__ __align__(8) uint64_t empty[LS_STAGES];
+    __shared__ double red_pos[LS_ROWS / 32];
+    __shared__ unsigned long long red_nz[LS_ROWS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t pred_bytes = ((size_t)LS_ROWS * W * sizeof(float) + 127) & ~(size_t)127;
+    const size_t true_bytes = ((size_t)LS_ROWS * W * sizeof(TrueT) + 127) & ~(size_t)127;
+    const size_t stage_bytes = pred_bytes + true_bytes;
+    if (tid == 0) {
+        for (int s = 0; s < LS_STAGES; ++s) { ls_mbar_init(&full[s], 1); ls_mbar_init(&empty[s], LS_ROWS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n_tiles = (n_boxes + LS_ROWS - 1) / LS_ROWS;
+    const long long per = n_tiles / gridDim.x, extra = n_tiles - per * gridDim.x;
+    const long long t_begin = (long long)blockIdx.x * per + min((long long)blockIdx.x, extra);
+    const long long t_end = t_begin + per + ((long long)blockIdx.x < extra ? 1 : 0);
+    if (warp == LS_ROWS / 32) {
+        // ---- producer warp ----
+        if (lane == 0) {
+            int it = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++it) {
+                const int s = it % LS_STAGES;
+                if (it >= LS_STAGES) ls_mbar_wait(&empty[s], (uint32_t)(((it / LS_STAGES) - 1) & 1));
+                const long long r0 = t * LS_ROWS;
+                const int rows = (int)min((long long)LS_ROWS, n_boxes - r0);
+                const uint32_t pb = (uint32_t)((size_t)rows * W * sizeof(float)), tb = (uint32_t)((size_t)rows * W * sizeof(TrueT));
+                unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+                ls_mbar_expect_tx(&full[s], pb + tb);
+                ls_tma_load_1d(dst, y_pred + r0 * W, pb, &full[s]);
+                ls_tma_load_1d(dst + pred_bytes, y_true + r0 * W, tb, &full[s]);
+            }
+        }
+        return;
+    }
+    // ---- consumer warps ----
+    double my_pos = 0.0;
+    unsigned long long my_nz = 0;
+    int it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % LS_STAGES;
+        ls_mbar_wait(&full[s], (uint32_t)((it / LS_STAGES) & 1));
+        const long long r0 = t * LS_ROWS;
+        const int rows = (int)min((long long)LS_ROWS, n_boxes - r0);
+        const unsigned char* src = smem_raw + (size_t)s * stage_bytes;
+        loss_rows<TrueT>(reinterpret_cast<const float*>(src), reinterpret_cast<const TrueT*>(src + pred_bytes), tid, rows, r0,
+                         n_boxes, A, C, W, closs, nl, img_pos, img_loc, my_pos, my_nz);
+        __syncwarp();
+        if (lane == 0) ls_mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { my_pos += __shfl_xor_sync(0xffffffffu, my_pos, o); my_nz += __shfl_xor_sync(0xffffffffu, my_nz, o); }
+    if (lane == 0) { red_pos[warp] = my_pos; red_nz[warp] = my_nz; }
+    // (the producer warp has left: a named barrier over the consumer warps only)
+    asm volatile("bar.sync 1, %0;" :: "n"(LS_ROWS) : "memory");
     if (tid == 0) {
         double p = 0.0; unsigned long long z = 0;
         for (int w = 0; w < LS_ROWS / 32; ++w) { p += red_pos[w]; z += red_nz[w]; }
@@ -345,7 +460,27 @@ extern "C" int ssdc_ssd_loss(ssdc_ctx* ctx, const void* y_true, int dtype_true, 
     int* quota = reinterpret_cast<int*>(base + o_q);
     float* d_out = reinterpret_cast<float*>(base + o_out);
     SSDC_CUDA(cudaMemsetAsync(base + o_sum, 0, (o_eq - o_sum), st));            // sums + state
-    {
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(d_true) | reinterpret_cast<uintptr_t>(d_pred)) % 16 == 0) && (n_boxes % 4 == 0) &&
+                        getenv("SSDC_LOSS_NO_TMA") == nullptr;
+    if (tma_ok) {
+        LaunchScope ls(ctx, &d, SSDC_K_THIN);
+        const size_t tsz = (dtype_true == SSDC_F32) ? 4 : 8;
+        const size_t stage = (((size_t)LS_ROWS * W * 4 + 127) & ~(size_t)127) + (((size_t)LS_ROWS * W * tsz + 127) & ~(size_t)127);
+        const size_t smem = stage * LS_STAGES;
+        int ctas_per_sm = (int)((224 * 1024) / (smem + 2048));
+        if (ctas_per_sm > 4) ctas_per_sm = 4;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const long long tiles = (n_boxes + LS_ROWS - 1) / LS_ROWS;
+        const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)d.sm_count * ctas_per_sm);
+        if (dtype_true == SSDC_F32) {
+            SSDC_CUDA(cudaFuncSetAttribute(loss_box_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            loss_box_tma_kernel<float><<<grid, LS_ROWS + 32, smem, st>>>((const float*)d_true, d_pred, n_boxes, (int)A, C, W, closs, nl, img_pos, img_loc, stt);
+        } else {
+            SSDC_CUDA(cudaFuncSetAttribute(loss_box_tma_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            loss_box_tma_kernel<double><<<grid, LS_ROWS + 32, smem, st>>>((const double*)d_true, d_pred, n_boxes, (int)A, C, W, closs, nl, img_pos, img_loc, stt);
+        }
+        SSDC_TRY(check_launch("loss_box_tma_kernel"));
+    } else {
         LaunchScope ls(ctx, &d, SSDC_K_THIN);
         const size_t smem = (size_t)LS_ROWS * W * 2 * sizeof(float);
         const long long tiles = (n_boxes + LS_ROWS - 1) / LS_ROWS;

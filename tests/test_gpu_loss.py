@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
+@pytest.fixture(autouse=True, params=['tma', 'ldg'])
+def loss_path(request, monkeypatch):
+    """Both loaders of the box kernel: TMA ring (default) and the plain tile copy (unaligned inputs)."""
+    if request.param == 'ldg':
+        monkeypatch.setenv('SSDC_LOSS_NO_TMA', '1')
+    return request.param
+
+
 def make_batch(layout, B, seed, bg_bias=3.0):
     kw = synth.layout_kwargs(layout)
     enc = orc.SSDInputEncoder(**kw)
