@@ -892,9 +892,17 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
             for (int shift = 56; shift >= 0; shift -= 8) {
                 for (int i = tid; i < 256; i += SW_THREADS) hist[i] = 0;
                 __syncthreads();
-                for (int i = tid; i < n; i += SW_THREADS) {
-                    const unsigned long long k = gk[i];
-                    if (k < hi && (k & pmask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+                // (four independent loads in flight per thread: the pass is bound by the L2 round trip)
+                for (int i0 = tid; i0 < n; i0 += 8 * SW_THREADS) {
+                    unsigned long long k4[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * SW_THREADS;
+                        k4[u] = (i < n) ? gk[i] : ~0ull;                 // (~0: never below `hi`)
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (k4[u] < hi && (k4[u] & pmask) == prefix) atomicAdd(&hist[(unsigned)(k4[u] >> shift) & 255u], 1u);
                 }
                 __syncthreads();
                 if (warp == 0) {
@@ -938,16 +946,24 @@ sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict_
         // compact {tau <= key < hi} into shared memory
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += SW_THREADS) {
-            const int i = i0 + tid;
-            const unsigned long long k = (i < n) ? gk[i] : 0ull;
-            const bool take = (i < n) && k >= tau && k < hi;
-            const unsigned m = __ballot_sync(0xffffffffu, take);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) ck[base + __popc(m & lt)] = k;
+        for (int i0 = 0; i0 < n; i0 += 8 * SW_THREADS) {
+            unsigned long long k4[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * SW_THREADS + tid;
+                k4[u] = (i < n) ? gk[i] : ~0ull;                         // (~0: never below `hi`)
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned long long k = k4[u];
+                const bool take = k >= tau && k < hi;
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (m) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) ck[base + __popc(m & lt)] = k;
+                }
             }
         }
         __syncthreads();
