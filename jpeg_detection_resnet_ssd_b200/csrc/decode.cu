@@ -266,7 +266,7 @@ decode_filter_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr,
                      int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
                      SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
     constexpr int V = 16 / (int)sizeof(InT);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = g.W, A = g.A;
     InT* tile = reinterpret_cast<InT*>(smem_raw);
     const int tid = threadIdx.x;
@@ -445,7 +445,7 @@ template <typename KeyT, bool IN_SMEM>
 __global__ void sort_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count,
                             const int* __restrict__ list, int* __restrict__ counters, int bin,
                             DecodeArgs g, KeyT* __restrict__ scratch, int scratch_stride) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_idx;
     KeyT* s = IN_SMEM ? reinterpret_cast<KeyT*>(smem_raw) : scratch + (size_t)blockIdx.x * scratch_stride;
     const int total = counters[CNT_LIST + bin];
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32)
 nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __restrict__ kept_count,
            const int* __restrict__ list, int* __restrict__ counters,
            const SBox<StoreT>* __restrict__ boxes, DecodeArgs g, int KS) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-warp shared memory: raw corners of the kept boxes (cache) and of the step's candidates,
     // the sort buffer, the pair queue and the per-candidate suppression masks
@@ -1289,7 +1289,7 @@ emit_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_count,
             const SBox<StoreT>* __restrict__ boxes, const int* __restrict__ aux_class, DecodeArgs g,
             Key128* __restrict__ merge_scratch, int merge_stride,
             double* __restrict__ rows, int* __restrict__ anchors) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int NS = g.NS;
     const int cnt = out_count[b];
@@ -1409,7 +1409,7 @@ emit_merge_kernel(const KeyT* __restrict__ keys, const int* __restrict__ kept_co
                   int Kcap, double* __restrict__ rows, int* __restrict__ anchors) {
     typedef Comp<KeyT> CK;
     typedef typename CK::type ck_t;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     KeyT* sk = reinterpret_cast<KeyT*>(smem_raw);
     const int b = blockIdx.x, lane = threadIdx.x;
     const int NS = g.NS;

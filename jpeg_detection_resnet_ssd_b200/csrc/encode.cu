@@ -216,7 +216,6 @@ __global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, 
 // ---------------------------------------------------------------------------
 // E1: per GT row, best anchor inside one chunk of anchors
 // ---------------------------------------------------------------------------
-constexpr int E1_GROUP = 64;      // GT rows reduced per block-level pass
 
 constexpr int E1_ROWS = 4;          // GT rows screened per barrier round
 
@@ -976,7 +975,7 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
             const float* __restrict__ gtau, int* __restrict__ cand, int* __restrict__ lcnt,
             double* __restrict__ lval, int* __restrict__ lidx, int* __restrict__ img_irr,
             int* __restrict__ plist, int* __restrict__ pcount) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int b = blockIdx.y, nblk = gridDim.x, blk = blockIdx.x;
     const long long g0 = gt_off[b];
     const int m = (int)(gt_off[b + 1] - g0);
@@ -1117,7 +1116,7 @@ greedy_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_o
               const float* __restrict__ gtau, const int* __restrict__ lcnt, const double* __restrict__ lval, const int* __restrict__ lidx,
               const int* __restrict__ img_irr, int* __restrict__ cand, int* __restrict__ match,
               int* __restrict__ plist, int* __restrict__ pcount) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_val[EG_WARPS];
     __shared__ int red_idx[EG_WARPS];
     __shared__ int s_round, s_more, s_cut2, s_ln;

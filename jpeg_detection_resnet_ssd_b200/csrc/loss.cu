@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(LS_ROWS)
 loss_box_kernel(const TrueT* __restrict__ y_true, const float* __restrict__ y_pred, long long n_boxes, int A, int C, int W,
                 float* __restrict__ closs, float* __restrict__ nl, double* __restrict__ img_pos, double* __restrict__ img_loc,
                 LossState* __restrict__ st) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sp = reinterpret_cast<float*>(smem_raw);             // LS_ROWS x W   predictions
     float* stt = sp + (size_t)LS_ROWS * W;                      // LS_ROWS x W   targets, float32 like the Keras placeholder
     __shared__ double red_pos[LS_ROWS / 32];

@@ -36,7 +36,7 @@ __global__ void voc_key_kernel(const float* __restrict__ conf, const long long* 
 __global__ void __launch_bounds__(1024)
 voc_sort_kernel(Key64* __restrict__ keys, const long long* __restrict__ cls_off, Key64* __restrict__ scratch,
                 const long long* __restrict__ scratch_off) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int c = blockIdx.x + 1;
     const long long p0 = cls_off[c];
     const int n = (int)(cls_off[c + 1] - p0);
