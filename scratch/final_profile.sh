@@ -7,3 +7,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"decode_filter_tma|sweep_kernel" -s 6 -c 2 -o gpurun_out/r01_e_decode_full -f python scratch/d1_prof.py > gpurun_out/ncu_c.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"template_tma|pair_kernel|greedy_kernel|seed_kernel|apply_list" -s 10 -c 5 -o gpurun_out/r01_e_encode_full -f python scratch/enc_prof.py 1024 2 > gpurun_out/ncu_d.log 2>&1
 ls -la gpurun_out | tail -12
+python scratch/loss_prof.py || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r01_e_launches_loss.csv python scratch/loss_prof.py > gpurun_out/ncu_e.log 2>&1
