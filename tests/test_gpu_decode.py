@@ -321,3 +321,22 @@ def test_device_resident_results(ctx):
     rc = lib.ssdc_decode_results_dev(ctx.handle, 0, C.byref(rows_p), None, None, None, None, None)
     assert rc == _lib.ERR_STATE
     ctx.dev_free(d_y)
+
+
+@pytest.mark.parametrize('top_k', [25, 'all'])
+def test_decode_many_classes(ctx, top_k):
+    """80 foreground classes (COCO-sized): more than one 32-class block per row in D1, composite keys with class
+    ids above 32, the wide k-way merge of the general path."""
+    kw = synth.layout_kwargs('tiny', n_classes=80)
+    enc = SSDInputEncoder(**kw)
+    C = 81
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 5, 19, bg_bias=4.0, hot=25)
+    H, W = kw['img_height'], kw['img_width']
+    dk = dict(confidence_thresh=0.01, iou_threshold=0.45, top_k=top_k, input_coords='centroids',
+              normalize_coords=True, img_height=H, img_width=W)
+    want, want_counts = to_rows7(orc.decode_detections(y, exp_mode='cr', with_anchor_index=True, **dk))
+    rows, counts, idx = _lib.run_decode(y, _lib.MODE_PER_CLASS, 0.01, 0.45, 0 if top_k == 'all' else top_k, 'centroids', True, H, W,
+                                        'half', ctx=ctx)
+    got, got_counts = product_rows7(rows, counts, idx)
+    assert want_counts.sum() > 20 and int(want[:, 1].max()) > 40
+    compare_rows(got, got_counts, want, want_counts, exact_coords=True)
