@@ -992,6 +992,7 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
     float* scut = stau + me;                                               // m   below this bound a pair cannot matter
     int* sreg = reinterpret_cast<int*>(scut + me);                         // m   row is regular
     float* scarea = reinterpret_cast<float*>(sreg + me);                   // K   lower bound of the class's area term
+    unsigned* cneed = reinterpret_cast<unsigned*>(scarea + EF_MAX_K);      // K x 4  rows for which the class can matter (bit masks)
     const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
     const float thr_cut = cut_of(thr_min);
     for (int r = tid; r < m; r += EP_THREADS) {
@@ -1006,6 +1007,15 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
         ub[e] = shape_bound(gtp + g0 + r, f.cls[k]);
     }
     for (int k = tid; k < K; k += EP_THREADS) scarea[k] = f.cls[k].z;
+    __syncthreads();
+    // per class: the rows whose shape bound reaches a threshold or their list level (fixed for the whole image, so a
+    // class nobody needs costs one shared-memory load per group)
+    for (int e = tid; e < K * 4; e += EP_THREADS) {
+        const int k = e >> 2, j = e & 3;
+        unsigned mk = 0;
+        for (int r = 32 * j; r < min(m, 32 * j + 32); ++r) mk |= (unsigned)(!(ub[r * K + k] < scut[r])) << (r & 31);
+        cneed[e] = mk;
+    }
     __syncthreads();
 
     bool irr = false;
@@ -1026,6 +1036,8 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
             const int gn = gidx + gstep;
             if (gn < ngroups) { k_n = f.grp_cls[gn]; gbox_n = f.grp_box[gn]; a_n = f.perm[gn * 32 + lane]; af_n = f.pboxf[gn * 32 + lane]; }
         }
+        const unsigned* cm = cneed + 4 * k;
+        if ((cm[0] | cm[1] | cm[2] | cm[3]) == 0u) continue;      // no row of this image can do anything with this class
         const float aarea = scarea[k];
         const bool live = a >= 0;
         Box<double> ab;
@@ -1033,14 +1045,13 @@ pair_kernel(const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off
         double cv = -INFINITY;
         int cg = 0x7fffffff;
         for (int r0 = 0; r0 < m; r0 += 32) {
+            const unsigned want = cm[r0 >> 5];
+            if (!want) continue;
             const int rl = r0 + lane;
-            bool need = false;
-            if (rl < m) {
-                // the class can matter for the row: its shape bound reaches a threshold or the row's list level ...
-                need = !(ub[rl * K + k] < scut[rl]);
-                // ... and the row touches this group of anchors at all (else every iou of the group is +0)
-                if (sreg[rl] && screen_disjoint(sgf[rl], gbox)) need = false;
-            }
+            // the class can matter for the row (its shape bound reaches a threshold or the row's list level) and the row
+            // touches this group of anchors at all (else every iou of the group is +0)
+            bool need = (want >> lane) & 1u;
+            if (need && sreg[rl] && screen_disjoint(sgf[rl], gbox)) need = false;
             unsigned rows = __ballot_sync(0xffffffffu, need);
             while (rows) {
                 const int r = r0 + __ffs(rows) - 1;
@@ -1662,7 +1673,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
                 const size_t mm = ((size_t)max_m + 1) & ~(size_t)1;
-                const size_t smem = mm * (sizeof(Box<double>) + sizeof(float4) + 3 * sizeof(float) + sizeof(int)) + mm * f.K * sizeof(float) + EF_MAX_K * sizeof(float) + 32;
+                const size_t smem = mm * (sizeof(Box<double>) + sizeof(float4) + 3 * sizeof(float) + sizeof(int)) + mm * f.K * sizeof(float) + EF_MAX_K * (sizeof(float) + 4 * sizeof(unsigned)) + 32;
                 dim3 grid((unsigned)nblk, (unsigned)B);
                 SSDC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 pair_kernel<<<grid, EP_THREADS, smem, st>>>(gtp, gt_off, f, g, gtau, cand, lcnt, lval, lidx, img_irr, plist, pcount);
