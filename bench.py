@@ -67,7 +67,8 @@ def load_peaks():
 
 def make_workload(batch, unique, bg_bias, seed, pinned):
     """Synthetic SSD300 y_pred (batch, 8732, 33) float32.  `unique` distinct images tiled."""
-    from jpeg_detection_resnet_ssd_b200 import synth, pinned_empty
+    import synth
+    from jpeg_detection_resnet_ssd_b200 import pinned_empty
     from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
     enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
     anchors = synth.anchors_of(enc)
@@ -383,7 +384,7 @@ def main():
 def extra_numbers(ctx, _lib, enc, peak):
     """Secondary numbers (not the headline): the encoder at BASELINE configs[1] (B=32) and at a large
     batch, device-timed, with the write kernel's roofline."""
-    from jpeg_detection_resnet_ssd_b200 import synth
+    import synth
     lib = ctx.lib
     out = {}
     ctx2, h = enc._encoder()
@@ -501,7 +502,7 @@ def extra_numbers(ctx, _lib, enc, peak):
 def loss_numbers(ctx, _lib, enc, peak):
     """`ssdc_ssd_loss` with both tensors resident on the device: y_true = the encoder's float64 output,
     y_pred = synthetic float32 predictions (64 unique images tiled)."""
-    from jpeg_detection_resnet_ssd_b200 import synth
+    import synth
     lib = ctx.lib
     B, A, W = 1024, A_SSD300, 33
     ctx2, h = enc._encoder()

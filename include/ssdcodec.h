@@ -83,6 +83,20 @@ void ssdc_destroy(ssdc_ctx* ctx);
 int  ssdc_ctx_num_devices(const ssdc_ctx* ctx);
 int  ssdc_synchronize(ssdc_ctx* ctx);
 
+/* Per-context options (test / diagnosis switches; none changes a result).  Unknown option: SSDC_ERR_ARG. */
+#define SSDC_OPT_NO_SWEEP          0  /* 1: decode_detections runs the general per-class pipeline instead of the image sweep */
+#define SSDC_OPT_FLOOR_TARGET      1  /* image sweep: number of best candidates per image that D1 always keeps complete
+                                         (speculative score floor, exact fallback below it); 0 = default (4096)        */
+#define SSDC_OPT_ENC_GENERAL       2  /* 1: encoder takes the general matching path                                    */
+#define SSDC_OPT_ENC_NO_OVERLAP    3  /* 1: encoder writes y_encoded with the fused write kernel (no template stream)  */
+#define SSDC_OPT_ENC_DENSE_PATCH   4  /* 1: encoder patches from the dense match array instead of the position list    */
+#define SSDC_OPT_LOSS_NO_TMA       5  /* 1: loss uses the plain tile-copy loader                                       */
+#define SSDC_OPT_H2D_CHUNK_MB      6  /* host input of ssdc_decode_submit is copied in chunks of this many MiB, each chunk
+                                         filtered (D1) while the next one is in flight; 0 = default (64), <0 = one copy */
+#define SSDC_OPT_COUNT             7
+int     ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value);
+int64_t ssdc_get_option(const ssdc_ctx* ctx, int option);
+
 /* Kernel launches issued by this context since creation (bench: gpu_launches). */
 int64_t ssdc_launch_count(const ssdc_ctx* ctx);
 

@@ -23,6 +23,8 @@ MODE_PER_CLASS, MODE_FAST, MODE_LAYER, MODE_LAYER_FAST = 0, 1, 2, 3
 CONVERSIONS = {'minmax2centroids': 0, 'centroids2minmax': 1, 'corners2centroids': 2,
                'centroids2corners': 3, 'minmax2corners': 4, 'corners2minmax': 5}
 IOU_OUTER, IOU_ELEMENTWISE = 0, 1
+OPTIONS = {'no_sweep': 0, 'floor_target': 1, 'enc_general': 2, 'enc_no_overlap': 3, 'enc_dense_patch': 4,
+           'loss_no_tma': 5, 'h2d_chunk_mb': 6}
 K_NAMES = ['decode_filter', 'plan', 'sort', 'nms', 'merge', 'enc_rowbest', 'enc_match', 'enc_write', 'thin', 'enc_patch']
 K_COUNT = len(K_NAMES)
 
@@ -63,6 +65,8 @@ SIGNATURES = {
     'ssdc_destroy': (None, [_vp]),
     'ssdc_ctx_num_devices': (_i, [_vp]),
     'ssdc_synchronize': (_i, [_vp]),
+    'ssdc_set_option': (_i, [_vp, _i, _i64]),
+    'ssdc_get_option': (_i64, [_vp, _i]),
     'ssdc_launch_count': (_i64, [_vp]),
     'ssdc_profile_enable': (_i, [_vp, _i]),
     'ssdc_profile_read': (_i, [_vp, C.POINTER(C.c_double), _pi64]),
@@ -158,6 +162,12 @@ class Context(object):
         except Exception:
             pass
 
+    def set_option(self, name, value):
+        """Test / diagnosis switches of the context (`OPTIONS`; include/ssdcodec.h SSDC_OPT_*); returns the old value."""
+        old = int(self.lib.ssdc_get_option(self.handle, OPTIONS[name]))
+        check(self.lib.ssdc_set_option(self.handle, OPTIONS[name], int(value)))
+        return old
+
     # -- measurement helpers (bench.py / tests) --
     def synchronize(self):
         check(self.lib.ssdc_synchronize(self.handle))
@@ -198,27 +208,26 @@ class Context(object):
 
 
 def pinned_empty(shape, dtype):
-    """numpy array backed by page-locked host memory (freed with the array)."""
+    """numpy array backed by page-locked host memory.
+
+    The memory is released when the LAST array referring to it dies: the finalizer hangs on the ctypes buffer
+    object at the end of every view's `.base` chain (`y[:n]`, `y.reshape(..)`, `np.asarray(y)` all keep it
+    alive), not on the array object returned here."""
+    import weakref
     lib = load_library()
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
+    count = int(np.prod(shape))
+    n = count * dtype.itemsize
     p = C.c_void_p()
     check(lib.ssdc_host_alloc(max(n, 1), C.byref(p)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[id(buf)] = (buf, p)
-    import weakref
-    weakref.finalize(arr, _free_pinned, id(buf))
-    return arr
+    weakref.finalize(buf, _free_pinned, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
-_PINNED = {}
-
-
-def _free_pinned(key):
-    ent = _PINNED.pop(key, None)
-    if ent is not None and _lib is not None:
-        _lib.ssdc_host_free(ent[1])
+def _free_pinned(address):
+    if _lib is not None:
+        _lib.ssdc_host_free(C.c_void_p(address))
 
 
 def default_devices():

@@ -66,13 +66,13 @@ int ssdc_init(const int* device_ids, int n_devices, ssdc_ctx** out) {
         d.device = device_ids[i];
         if (d.device < 0 || d.device >= avail) {
             set_error("ssdc_init: device id %d out of range (have %d)", d.device, avail);
-            delete ctx; return SSDC_ERR_ARG;
+            ssdc_destroy(ctx); return SSDC_ERR_ARG;
         }
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, d.device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); delete ctx; return SSDC_ERR_CUDA; }
+        if (cudaGetDeviceProperties(&prop, d.device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); ssdc_destroy(ctx); return SSDC_ERR_CUDA; }
         if (prop.major != 10) {
             set_error("ssdc_init: device %d is sm_%d%d; libssdcodec is built for sm_100a (B200) only", d.device, prop.major, prop.minor);
-            delete ctx; return SSDC_ERR_NODEVICE;
+            ssdc_destroy(ctx); return SSDC_ERR_NODEVICE;
         }
         d.sm_count = prop.multiProcessorCount;
         if (cudaSetDevice(d.device) != cudaSuccess ||
@@ -82,7 +82,7 @@ int ssdc_init(const int* device_ids, int n_devices, ssdc_ctx** out) {
             cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreate(&d.t0) != cudaSuccess || cudaEventCreate(&d.t1) != cudaSuccess) {
             set_error("ssdc_init: stream/event creation failed on device %d: %s", d.device, cudaGetErrorString(cudaGetLastError()));
-            delete ctx; return SSDC_ERR_CUDA;
+            ssdc_destroy(ctx); return SSDC_ERR_CUDA;
         }
     }
     *out = ctx;
@@ -91,7 +91,9 @@ int ssdc_init(const int* device_ids, int n_devices, ssdc_ctx** out) {
 
 void ssdc_destroy(ssdc_ctx* ctx) {
     if (!ctx) return;
+    { std::lock_guard<std::mutex> lk(ctx->mu); }       // a call still running on another thread finishes first
     for (DevCtx& d : ctx->devs) {
+        if (d.device < 0) continue;
         cudaSetDevice(d.device);
         if (d.stream2) cudaStreamSynchronize(d.stream2);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -99,7 +101,7 @@ void ssdc_destroy(ssdc_ctx* ctx) {
                        &d.out_anchor, &d.out_count, &d.row_offset, &d.pad_rows, &d.pad_anchor, &d.gt, &d.gt_off, &d.partial, &d.matches,
                        &d.enc_out, &d.enc_out2, &d.enc_idx, &d.enc_flags, &d.t0buf, &d.t1buf, &d.t2buf, &d.t3buf};
         for (Buf* b : bufs) b->release();
-        d.h_small.release();
+        for (int i = 0; i < DevCtx::H_RING; ++i) { d.h_ring[i].release(); if (d.h_ev[i]) cudaEventDestroy(d.h_ev[i]); }
         if (d.t0) cudaEventDestroy(d.t0);
         if (d.t1) cudaEventDestroy(d.t1);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
@@ -122,6 +124,17 @@ int ssdc_synchronize(ssdc_ctx* ctx) {
         SSDC_CUDA(cudaStreamSynchronize(d.stream));
     }
     return SSDC_OK;
+}
+
+int ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value) {
+    if (!ctx || option < 0 || option >= SSDC_OPT_COUNT) { set_error("ssdc_set_option: bad context / unknown option %d", option); return SSDC_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->opt[option] = value;
+    return SSDC_OK;
+}
+int64_t ssdc_get_option(const ssdc_ctx* ctx, int option) {
+    if (!ctx || option < 0 || option >= SSDC_OPT_COUNT) return 0;
+    return ctx->opt[option];
 }
 
 int64_t ssdc_launch_count(const ssdc_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }

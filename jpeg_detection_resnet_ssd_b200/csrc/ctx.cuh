@@ -96,7 +96,38 @@ struct DevCtx {
     // decode scratch
     Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
     Buf pad_rows, pad_anchor;        // image-sweep path: (B, top_k, 6) float64 rows + anchor ids, as the sweep leaves them
-    PinnedBuf h_small;
+    // small pinned staging areas for asynchronous H2D copies of per-call host data: a ring guarded by events, so a
+    // call that only enqueues work never overwrites bytes an earlier call's copy has not read yet
+    static constexpr int H_RING = 4;
+    PinnedBuf h_ring[H_RING];
+    cudaEvent_t h_ev[H_RING] = {nullptr, nullptr, nullptr, nullptr};
+    bool h_busy[H_RING] = {false, false, false, false};
+    int h_next = 0;
+    // Stages `bytes` of per-call host data: returns a pinned area the caller fills and then copies from with
+    // cudaMemcpyAsync on `stream`, followed by staged_done().
+    int stage_acquire(size_t bytes, void** out, int* slot_out) {
+        const int s = h_next;
+        h_next = (h_next + 1) % H_RING;
+        if (h_busy[s]) {
+            cudaError_t e = cudaEventSynchronize(h_ev[s]);
+            if (e != cudaSuccess) { set_error("cudaEventSynchronize(staging) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
+            h_busy[s] = false;
+        }
+        int r = h_ring[s].ensure(bytes);
+        if (r != SSDC_OK) return r;
+        *out = h_ring[s].p; *slot_out = s;
+        return SSDC_OK;
+    }
+    int stage_done(int s, cudaStream_t st) {
+        if (!h_ev[s]) {
+            cudaError_t e = cudaEventCreateWithFlags(&h_ev[s], cudaEventDisableTiming);
+            if (e != cudaSuccess) { set_error("cudaEventCreate(staging) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
+        }
+        cudaError_t e = cudaEventRecord(h_ev[s], st);
+        if (e != cudaSuccess) { set_error("cudaEventRecord(staging) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
+        h_busy[s] = true;
+        return SSDC_OK;
+    }
     DecodeJob job;
     // encode scratch
     Buf gt, gt_off, partial, matches, enc_out, enc_out2, enc_idx, enc_flags;
@@ -110,6 +141,7 @@ struct ssdc_ctx {
     std::vector<ssdc::DevCtx> devs;
     std::mutex mu;
     std::atomic<int64_t> launches{0};
+    int64_t opt[SSDC_OPT_COUNT] = {0};
     bool profile = false;
     double prof_ms[SSDC_K_COUNT];
     int64_t prof_n[SSDC_K_COUNT];

@@ -1551,15 +1551,23 @@ static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int
     const int64_t n = last - first;
     *n_gt = n;
     SSDC_TRY(d->gt_off.ensure((size_t)(B + 1) * sizeof(long long)));
-    SSDC_TRY(d->h_small.ensure((size_t)(B + 1) * sizeof(long long)));
-    long long* h = d->h_small.as<long long>();
+    // Offsets and rows are staged in ONE pinned area of the event-guarded ring: a call that only enqueues work
+    // (on_device outputs) may return before the copies ran, and neither the next call nor the caller's own reuse
+    // of `gt` may change the bytes they read.
+    const size_t off_bytes = (((size_t)(B + 1) * sizeof(long long)) + 63) & ~(size_t)63;
+    const size_t gt_bytes = (size_t)n * 5 * sizeof(double);
+    void* hp = nullptr; int hs = 0;
+    SSDC_TRY(d->stage_acquire(off_bytes + gt_bytes, &hp, &hs));
+    long long* h = reinterpret_cast<long long*>(hp);
     for (int64_t i = 0; i <= B; ++i) h[i] = gt_offsets[b0 + i] - first;
     SSDC_CUDA(cudaMemcpyAsync(d->gt_off.p, h, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->stream));
     if (n > 0) {
         SSDC_TRY(d->gt.ensure((((size_t)n * 5 * sizeof(double) + 63) & ~(size_t)63) + (size_t)n * sizeof(GtPrep)));
-        SSDC_CUDA(cudaMemcpyAsync(d->gt.p, gt + first * 5, (size_t)n * 5 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        char* hg = reinterpret_cast<char*>(hp) + off_bytes;
+        memcpy(hg, gt + first * 5, gt_bytes);
+        SSDC_CUDA(cudaMemcpyAsync(d->gt.p, hg, gt_bytes, cudaMemcpyHostToDevice, d->stream));
     }
-    return SSDC_OK;
+    return d->stage_done(hs, d->stream);
 }
 
 int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B,
@@ -1583,10 +1591,14 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
                         (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)ET_ROWS * row_bytes) % 16 == 0) &&
                         ((((size_t)enc->A % ET_ROWS) * row_bytes) % 16 == 0);
-    const bool no_overlap = getenv("SSDC_ENC_NO_OVERLAP") != nullptr;      // (diagnostic switches, read per call)
+    const bool no_overlap = ctx->opt[SSDC_OPT_ENC_NO_OVERLAP] != 0;
     const size_t smem_tpl = (size_t)ET_ROWS * row_bytes * (y2_dev ? 2 : 1);
     const bool overlap = tma_ok && !no_overlap && smem_tpl <= 64 * 1024;
-    const int dbg = getenv("SSDC_ENC_DBG") ? atoi(getenv("SSDC_ENC_DBG")) : 0;      // (timing experiments only)
+#ifdef SSDC_TIMING_KNOBS
+    const int dbg = getenv("SSDC_ENC_DBG") ? atoi(getenv("SSDC_ENC_DBG")) : 0;      // (timing experiments only; not in release builds)
+#else
+    constexpr int dbg = 0;
+#endif
     if (overlap && dbg != 1) {
         // E3 template stream: independent of the ground truth, so it starts first and runs beside E1 / E2.
         // (With per-launch profiling on, everything stays on the main stream so that each kernel is timed alone.)
@@ -1619,13 +1631,13 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     // ---- sparse path: shape classes + fused matching, then a patch of the few rows that differ from the template
     const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
     const bool sparse = overlap && enc->fast_ok && max_m <= EF_MAX_M && thr_min > 0.0 && thr_min < INFINITY &&
-                        (!g.multi || g.pos_thr == g.pos_thr) && g.neg_thr == g.neg_thr && getenv("SSDC_ENC_GENERAL") == nullptr;
+                        (!g.multi || g.pos_thr == g.pos_thr) && g.neg_thr == g.neg_thr && ctx->opt[SSDC_OPT_ENC_GENERAL] == 0;
     if (sparse) {
         const long long total = (long long)B * enc->A;
         int* cand = midx_dev;
         if (!cand) { SSDC_TRY(d->matches.ensure((size_t)total * sizeof(int))); cand = d->matches.as<int>(); }
         if (n_gt > 0 || midx_dev) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
-        const bool use_plist = total < 0x7fffffffLL && getenv("SSDC_ENC_DENSE_PATCH") == nullptr;
+        const bool use_plist = total < 0x7fffffffLL && ctx->opt[SSDC_OPT_ENC_DENSE_PATCH] == 0;
         int* plist = nullptr;
         int* pcount = nullptr;
         if (n_gt > 0) {
@@ -1636,7 +1648,9 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             const int ngroups = f.n_slots / 32;
             // CTAs per image: enough CTAs to fill the device a few times over, at least one group per warp and step
             int nblk = (int)((6LL * d->sm_count + B - 1) / B);
+#ifdef SSDC_TIMING_KNOBS
             if (const char* e = getenv("SSDC_ENC_NBLK")) nblk = atoi(e);
+#endif
             if (nblk > ngroups / (EP_THREADS / 32)) nblk = ngroups / (EP_THREADS / 32);
             if (nblk > 16) nblk = 16;
             if (nblk < 1) nblk = 1;

@@ -461,7 +461,7 @@ extern "C" int ssdc_ssd_loss(ssdc_ctx* ctx, const void* y_true, int dtype_true, 
     float* d_out = reinterpret_cast<float*>(base + o_out);
     SSDC_CUDA(cudaMemsetAsync(base + o_sum, 0, (o_eq - o_sum), st));            // sums + state
     const bool tma_ok = ((reinterpret_cast<uintptr_t>(d_true) | reinterpret_cast<uintptr_t>(d_pred)) % 16 == 0) && (n_boxes % 4 == 0) &&
-                        getenv("SSDC_LOSS_NO_TMA") == nullptr;
+                        ctx->opt[SSDC_OPT_LOSS_NO_TMA] == 0;
     if (tma_ok) {
         LaunchScope ls(ctx, &d, SSDC_K_THIN);
         const size_t tsz = (dtype_true == SSDC_F32) ? 4 : 8;

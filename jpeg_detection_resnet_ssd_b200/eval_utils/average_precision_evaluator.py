@@ -94,6 +94,19 @@ class DeviceEvaluator(object):
                       if not ((l[g['ymax']] - l[g['ymin']]) * (l[g['xmax']] - l[g['xmin']]) < self.ignore_under_area)]
         return labels
 
+    def _neutral_of(self, i):
+        """Neutral flags of image i aligned with `_labels_of(i)`: the `ignore_under_area` filter is applied to the
+        flags too, in the recall denominators and in the matching alike (documented deviation: the reference filters
+        the labels only and then indexes the unfiltered flags, :551 / :711)."""
+        nb = np.asarray(self.data_generator.eval_neutral[i], dtype=bool).reshape(-1)
+        if self.ignore_under_area > 0:
+            g = self.gt_format
+            full = np.asarray(self.data_generator.labels[i], dtype=np.float64)
+            if full.size:
+                keep = ~((full[:, g['ymax']] - full[:, g['ymin']]) * (full[:, g['xmax']] - full[:, g['xmin']]) < self.ignore_under_area)
+                nb = nb[:len(keep)][keep]
+        return nb
+
     def get_num_gt_per_class(self, ignore_neutral_boxes=True, verbose=True, ret=False):
         """reference :494-568."""
         if self.data_generator.labels is None:
@@ -107,8 +120,7 @@ class DeviceEvaluator(object):
                 continue
             cls = boxes[:, ci].astype(int)
             if ignore_neutral_boxes and neutral is not None:
-                keep = ~np.asarray(neutral[i], dtype=bool)[:len(cls)]
-                cls = cls[keep]
+                cls = cls[~self._neutral_of(i)]
             np.add.at(counts, cls, 1)
         self.num_gt_per_class = counts
         if ret:
@@ -142,12 +154,7 @@ class DeviceEvaluator(object):
             if n:
                 gt_rows.append(lab[:, [g['class_id'], g['xmin'], g['ymin'], g['xmax'], g['ymax']]])
                 if use_neutral:
-                    nb = np.asarray(self.data_generator.eval_neutral[i], dtype=bool).reshape(-1)
-                    if self.ignore_under_area > 0:       # keep the flags aligned with the filtered labels
-                        full = np.asarray(self.data_generator.labels[i], dtype=np.float64)
-                        keep = ~((full[:, g['ymax']] - full[:, g['ymin']]) * (full[:, g['xmax']] - full[:, g['xmin']]) < self.ignore_under_area)
-                        nb = nb[keep]
-                    gt_neu.append(nb.astype(np.uint8))
+                    gt_neu.append(self._neutral_of(i).astype(np.uint8))
             gt_off[i + 1] = gt_off[i] + n
         gt = np.ascontiguousarray(np.concatenate(gt_rows, axis=0)) if gt_rows else np.zeros((0, 5))
         neu = np.ascontiguousarray(np.concatenate(gt_neu)) if (use_neutral and gt_neu) else None

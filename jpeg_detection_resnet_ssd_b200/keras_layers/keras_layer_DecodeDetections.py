@@ -8,21 +8,29 @@ The reference layer is float32 TensorFlow ops around `tf.image.non_max_suppressi
 "layer mode": float32 decode with the layer's operation order, `conf > float32(thresh)`,
 TensorFlow's float32 IoU, at most `nms_max_output_size` boxes per class, top-k by score with
 the lower (class, rank) index first on ties.  PARITY UNPINNED: TensorFlow is not available
-to execute the original, so this mode is checked against a CPU restatement only.
+to execute the original, so this mode is checked against a CPU restatement and TensorFlow's
+published NMS unit-test vectors only.
+
+Drop-in mode: the reference's models build their inference graph with this class
+(models/keras_ssd300_dct_j2d_resnet.py:42-43,885), so when the reference's own module is
+importable further down the package path (Keras / TensorFlow present) `DecodeDetections`
+IS the reference's Keras `Layer`, unchanged; the device callable is always available as
+`DeviceDecodeDetections` (e.g. on the raw output of a `model_mode='training'` model).
 """
 from __future__ import division
 
 import numpy as np
 
 try:
-    from .. import _lib
+    from .. import _lib, _dropin
 except ImportError:
     import _lib
+    import _dropin
 
 _MODE = _lib.MODE_LAYER
 
 
-class DecodeDetections(object):
+class DeviceDecodeDetections(object):
     def __init__(self,
                  confidence_thresh=0.01,
                  iou_threshold=0.45,
@@ -80,3 +88,7 @@ class DecodeDetections(object):
             'img_height': self.img_height,
             'img_width': self.img_width,
         }
+
+
+_ref = _dropin.load_shadowed(__package__ or 'keras_layers', 'keras_layer_DecodeDetections') if (__package__ or '').split('.')[0] == 'keras_layers' else None
+DecodeDetections = _ref.DecodeDetections if _ref is not None and hasattr(_ref, 'DecodeDetections') else DeviceDecodeDetections

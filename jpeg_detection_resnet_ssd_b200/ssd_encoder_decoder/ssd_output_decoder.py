@@ -41,8 +41,9 @@ def _nms_indices(boxes, scores, iou_threshold, coords, border_pixels):
     s = np.ascontiguousarray(scores, dtype=np.float64)
     keep = np.empty(max(n, 1), dtype=np.int32)
     k = _lib.C.c_int64(0)
-    _lib.check(ctx.lib.ssdc_greedy_nms(ctx.handle, _lib.ptr(b), _lib.ptr(s), n, float(iou_threshold),
-                                      _lib.COORDS[coords], _lib.BORDER[border_pixels], _lib.ptr(keep), _lib.C.byref(k)))
+    with ctx.call_lock:      # shares the decode scratch: never inside another thread's submit .. collect transaction
+        _lib.check(ctx.lib.ssdc_greedy_nms(ctx.handle, _lib.ptr(b), _lib.ptr(s), n, float(iou_threshold),
+                                          _lib.COORDS[coords], _lib.BORDER[border_pixels], _lib.ptr(keep), _lib.C.byref(k)))
     return keep[:k.value]
 
 

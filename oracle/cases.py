@@ -11,7 +11,7 @@ import hashlib
 
 import numpy as np
 
-from jpeg_detection_resnet_ssd_b200 import synth
+import synth
 
 
 def sha256_of(*arrays):

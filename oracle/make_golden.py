@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import cases, ref_loader                      # noqa: E402
 from oracle import ssd_codec_oracle as orc                # noqa: E402
-from jpeg_detection_resnet_ssd_b200 import synth          # noqa: E402
+import synth
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 EXP_PROBE = np.linspace(-3.0, 3.0, 4001).astype(np.float32)

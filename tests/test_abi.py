@@ -106,7 +106,7 @@ def test_argument_validation_before_device():
 def test_anchor_generation_matches_oracle():
     """Construction-time host configuration: product anchors == oracle anchors, bit for bit."""
     from oracle import ssd_codec_oracle as orc
-    from jpeg_detection_resnet_ssd_b200 import synth
+    import synth
     from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
     for layout, n in (('ssd300', 8732), ('ssd512', 24564), ('tiny', None)):
         for over in (dict(), dict(coords='corners'), dict(coords='minmax'), dict(clip_boxes=True), dict(normalize_coords=False)):
@@ -184,6 +184,10 @@ def test_drop_in_extends_partially_replaced_reference_classes(tmp_path):
     (fake / 'keras_loss_function').mkdir()
     (fake / 'keras_loss_function' / '__init__.py').write_text('')
     (fake / 'keras_loss_function' / 'keras_ssd_loss.py').write_text("class SSDLoss:\n    origin = 'reference'\n")
+    (fake / 'keras_layers').mkdir()
+    (fake / 'keras_layers' / '__init__.py').write_text('')
+    for name in ('DecodeDetections', 'DecodeDetectionsFast'):
+        (fake / 'keras_layers' / ('keras_layer_%s.py' % name)).write_text("class %s:\n    origin = 'reference'\n" % name)
     code = (
         "from eval_utils.average_precision_evaluator import Evaluator, DeviceEvaluator\n"
         "e = Evaluator()\n"
@@ -191,6 +195,12 @@ def test_drop_in_extends_partially_replaced_reference_classes(tmp_path):
         "assert Evaluator.match_predictions is DeviceEvaluator.match_predictions\n"
         "from keras_loss_function.keras_ssd_loss import SSDLoss, DeviceSSDLoss\n"
         "assert SSDLoss.origin == 'reference' and hasattr(DeviceSSDLoss, 'compute_loss')\n"
+        # the models build their inference graph with these classes (keras_ssd300_dct_j2d_resnet.py:42-43,885): the
+        # reference's Keras layers must come through, the device callables keep their own names
+        "from keras_layers.keras_layer_DecodeDetections import DecodeDetections, DeviceDecodeDetections\n"
+        "from keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast, DeviceDecodeDetectionsFast\n"
+        "assert DecodeDetections.origin == 'reference' and DecodeDetectionsFast.origin == 'reference'\n"
+        "assert hasattr(DeviceDecodeDetections, 'call') and issubclass(DeviceDecodeDetectionsFast, DeviceDecodeDetections)\n"
         "print('ok')\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'), str(fake)]))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)
@@ -198,6 +208,9 @@ def test_drop_in_extends_partially_replaced_reference_classes(tmp_path):
     # stand-alone (no reference on the path): the device classes
     code2 = ("from jpeg_detection_resnet_ssd_b200.eval_utils.average_precision_evaluator import Evaluator, DeviceEvaluator\n"
              "from jpeg_detection_resnet_ssd_b200.keras_loss_function.keras_ssd_loss import SSDLoss, DeviceSSDLoss\n"
+             "from jpeg_detection_resnet_ssd_b200.keras_layers.keras_layer_DecodeDetections import DecodeDetections, DeviceDecodeDetections\n"
+             "from jpeg_detection_resnet_ssd_b200.keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast, DeviceDecodeDetectionsFast\n"
+             "assert DecodeDetections is DeviceDecodeDetections and DecodeDetectionsFast is DeviceDecodeDetectionsFast\n"
              "assert Evaluator is DeviceEvaluator and SSDLoss is DeviceSSDLoss\nprint('ok')\n")
     r = subprocess.run([sys.executable, '-c', code2], capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]

@@ -5,7 +5,8 @@ import pytest
 
 from oracle import cases
 from oracle import ssd_codec_oracle as orc
-from jpeg_detection_resnet_ssd_b200 import _lib, synth
+import synth
+from jpeg_detection_resnet_ssd_b200 import _lib
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder as dec
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder_no_log as dec_nolog
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
@@ -228,11 +229,11 @@ def test_image_sweep_equals_per_class_pipeline(layout, bias, thr, ctx):
     y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 3, 77, bg_bias=bias, hot=40)
     for top_k in (200, 7):
         a = _lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, top_k, 'centroids', True, kw['img_height'], kw['img_width'], 'half', ctx=ctx)
-        os.environ['SSDC_NO_SWEEP'] = '1'
+        ctx.set_option('no_sweep', 1)
         try:
             b = _lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, top_k, 'centroids', True, kw['img_height'], kw['img_width'], 'half', ctx=ctx)
         finally:
-            del os.environ['SSDC_NO_SWEEP']
+            ctx.set_option('no_sweep', 0)
         ra, ca = product_rows7(*a)
         rb, cb = product_rows7(*b)
         assert np.array_equal(ca, cb) and np.array_equal(ra, rb)

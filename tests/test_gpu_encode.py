@@ -4,7 +4,7 @@ import pytest
 
 from oracle import cases
 from oracle import ssd_codec_oracle as orc
-from jpeg_detection_resnet_ssd_b200 import synth
+import synth
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_input_encoder as enc_mod
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_input_encoder_no_log as enc_nolog
 
@@ -16,17 +16,17 @@ OFFSET_RTOL = 1e-5    # north_star: encoded offsets within 1e-5 relative
 
 
 @pytest.fixture(autouse=True, params=['sparse', 'sparse_dense_patch', 'general', 'serial'])
-def enc_path(request, monkeypatch):
+def enc_path(request, ctx):
     """Every test runs through the encoder pipelines: shape-class sparse path (default; also with the patch
     kernel that scans the dense decision array instead of the position list), the general kernels beside
     the template stream, and the fully serial general kernels."""
-    if request.param == 'sparse_dense_patch':
-        monkeypatch.setenv('SSDC_ENC_DENSE_PATCH', '1')
-    elif request.param != 'sparse':
-        monkeypatch.setenv('SSDC_ENC_GENERAL', '1')
-    if request.param == 'serial':
-        monkeypatch.setenv('SSDC_ENC_NO_OVERLAP', '1')
-    return request.param
+    opts = {'sparse': {}, 'sparse_dense_patch': {'enc_dense_patch': 1}, 'general': {'enc_general': 1},
+            'serial': {'enc_general': 1, 'enc_no_overlap': 1}}[request.param]
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    yield request.param
+    for k in opts:
+        ctx.set_option(k, 0)
 
 
 def make(case):
@@ -199,3 +199,32 @@ def test_encode_low_thresholds_everything_matches(ctx, layout):
     C = kw['n_classes'] + 1
     assert np.array_equal(y[:, :, :C], yo[:, :, :C]) and np.array_equal(y[:, :, C + 4:], yo[:, :, C + 4:])
     assert rel_err(y, yo).max() <= OFFSET_RTOL
+
+
+def test_back_to_back_device_encodes_keep_their_own_ground_truth(ctx):
+    """`ssdc_encode` with device outputs only enqueues work: two calls with different ground truth and no
+    synchronisation in between must each be matched against their OWN rows and offsets (the pinned staging of the
+    per-call host data is an event-guarded ring), even when the caller reuses its host arrays right away."""
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    enc = synth.make_encoder(enc_mod.SSDInputEncoder, 'ssd300')
+    _, h = enc._encoder()
+    lib = ctx.lib
+    B, n = 8, 8 * 8732 * 33 * 8
+    batches = [synth.synth_ground_truth(300, 300, 20, B, seed=s, min_boxes=1 + 3 * s, max_boxes=3 + 3 * s) for s in range(6)]
+    want = [enc(gt) for gt in batches]
+    bufs = [ctx.dev_alloc(n) for _ in batches]
+    flat0, offs0 = synth.flatten_ground_truth(batches[-1])
+    flat = np.zeros((max(synth.flatten_ground_truth(g)[0].shape[0] for g in batches), 5))
+    offs = np.zeros(B + 1, np.int64)
+    for gt, d in zip(batches, bufs):
+        f, o = synth.flatten_ground_truth(gt)
+        flat[:f.shape[0]] = f          # the SAME host arrays are overwritten for every call
+        offs[:] = o
+        _lib.check(lib.ssdc_encode(h, _lib.ptr(flat), _lib.ptr(offs), B, 1, d, None, None))
+    flat[:] = 0.0
+    ctx.synchronize()
+    for w, d in zip(want, bufs):
+        got = np.empty_like(w)
+        ctx.d2h(got, d)
+        assert np.array_equal(got, w)
+        ctx.dev_free(d)

@@ -5,7 +5,7 @@ import pytest
 
 from oracle import ssd_loss_oracle as lo
 from oracle import ssd_codec_oracle as orc
-from jpeg_detection_resnet_ssd_b200 import synth
+import synth
 from jpeg_detection_resnet_ssd_b200.keras_loss_function.keras_ssd_loss import SSDLoss
 
 pytestmark = pytest.mark.gpu
@@ -13,11 +13,11 @@ RTOL = 1e-5
 
 
 @pytest.fixture(autouse=True, params=['tma', 'ldg'])
-def loss_path(request, monkeypatch):
+def loss_path(request, ctx):
     """Both loaders of the box kernel: TMA ring (default) and the plain tile copy (unaligned inputs)."""
-    if request.param == 'ldg':
-        monkeypatch.setenv('SSDC_LOSS_NO_TMA', '1')
-    return request.param
+    ctx.set_option('loss_no_tma', 1 if request.param == 'ldg' else 0)
+    yield request.param
+    ctx.set_option('loss_no_tma', 0)
 
 
 def make_batch(layout, B, seed, bg_bias=3.0):

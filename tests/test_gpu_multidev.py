@@ -4,7 +4,8 @@ the single-device results bit for bit.  Skipped on a single-GPU box."""
 import numpy as np
 import pytest
 
-from jpeg_detection_resnet_ssd_b200 import _lib, synth, Context, set_context
+import synth
+from jpeg_detection_resnet_ssd_b200 import _lib, Context, set_context
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
 
 pytestmark = pytest.mark.gpu

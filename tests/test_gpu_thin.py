@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import ssd_codec_oracle as orc
-from jpeg_detection_resnet_ssd_b200 import synth
+import synth
 from jpeg_detection_resnet_ssd_b200.bounding_box_utils import bounding_box_utils as bbu
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import matching_utils as mu
 from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder import ssd_output_decoder as dec

@@ -6,7 +6,7 @@ import pytest
 
 from oracle import cases, ref_loader
 from oracle import ssd_codec_oracle as orc
-from jpeg_detection_resnet_ssd_b200 import synth
+import synth
 
 from helpers import load_golden, host_exp_matches_golden, to_rows7, rel_err
 
