@@ -19,7 +19,7 @@ rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
 dist = bench.init_dist(world, int(os.environ['LOCAL_RANK']), backend='gloo')
 ms = bench.max_over_ranks(10.0 + 5.0 * rank, dist)          # rank 1 is the slow one
 dist.barrier()
-value = bench.whole_job_throughput(world, 1024, 4, ms)
+value = bench.whole_job_throughput(world * 1024, 4, ms)          # weak scaling: every rank brings 1024 images
 lo, hi = bench.shard_range(1000, world, rank)
 if rank == 0:
     print(json.dumps({'ms': ms, 'value': value, 'shard': [lo, hi]}))
@@ -78,3 +78,15 @@ def test_reference_arm_under_torchrun_world2():
     assert out['impl'] == 'reference' and out['unit'] == 'images/s' and out['value'] > 0
     assert out['cpu_baseline']['kind'] == 'port' and out['cpu_baseline']['cores'] >= 1
     assert out['e2e']['h2d_bytes_per_step'] == 0 and out['n_gpus'] == 2
+    assert out['config']['config_index'] == 2 and out['config']['batch_per_gpu'] == 1024
+
+
+def test_reference_arm_other_configs():
+    """Every BASELINE configuration has a CPU arm (encoder and round trip included)."""
+    for cfg in ('1', '4'):
+        r = subprocess.run([sys.executable, 'bench.py', '--impl', 'reference', '--config', cfg, '--steps', '1', '--warmup', '1'],
+                           capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+        assert out['impl'] == 'reference' and out['value'] > 0 and out['config']['config_index'] == int(cfg)
+        assert out['dtype'] == 'f64'

@@ -93,3 +93,63 @@ def test_keras_layer_contract(layer_cls, oracle_fn, ctx):
     assert layer.get_config()['top_k'] == 30
     with pytest.raises(ValueError):
         layer_cls(coords='corners', img_height=1, img_width=1)
+
+
+def _layer_input_from_tf_boxes(boxes_yxyx, scores, fast):
+    """(1, n, 14) float32 y_pred whose layer decode reproduces the given boxes: zero offsets, anchor = the box in
+    centroid form (negative sizes for flipped corners), class 1 confidence = the score."""
+    b = np.asarray(boxes_yxyx, np.float32).reshape(-1, 4)
+    n = b.shape[0]
+    y = np.zeros((1, n, 14), np.float32)
+    y[0, :, 1] = scores
+    y[0, :, 0] = np.asarray(scores, np.float32) - np.float32(1.0) if fast else 0.0
+    y[0, :, 6] = (b[:, 1] + b[:, 3]) / np.float32(2)       # cx
+    y[0, :, 7] = (b[:, 0] + b[:, 2]) / np.float32(2)       # cy
+    y[0, :, 8] = b[:, 3] - b[:, 1]                         # w (x2 - x1)
+    y[0, :, 9] = b[:, 2] - b[:, 0]                         # h
+    y[0, :, 10:] = [0.1, 0.1, 0.2, 0.2]
+    return y
+
+
+@pytest.mark.parametrize('mode', ['layer', 'layer_fast'])
+def test_device_layer_modes_reproduce_tensorflows_published_nms_answers(mode, ctx):
+    """The device layer modes on TensorFlow's own NMS unit-test cases (tests/golden/tf_nms_published.json): the
+    selected boxes, in selection order, are the published answers.  max_output_size below top_k takes the general
+    pipeline, at or above it the image sweep."""
+    import json
+    import os
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'tf_nms_published.json')) as fh:
+        vec = json.load(fh)
+    m = _lib.MODE_LAYER if mode == 'layer' else _lib.MODE_LAYER_FAST
+    for c in vec['cases']:
+        if not c['boxes']:
+            # (A = 0 is not a valid tensor shape at the C ABI: one box below the confidence threshold instead)
+            y = _layer_input_from_tf_boxes([[0, 0, 1, 1]], [-5.0], mode == 'layer_fast')
+        else:
+            y = _layer_input_from_tf_boxes(c['boxes'], c['scores'], mode == 'layer_fast')
+        for top_k in (4, 40):
+            rows, counts, idx = _lib.run_decode(y, m, -1.5, c['iou_threshold'], top_k, 'centroids', False, None, None, 'half',
+                                                log_wh=True, nms_cap=c['max_output_size'], ctx=ctx)
+            assert idx.tolist() == c['selected'][:top_k], (c['name'], top_k)
+            assert counts.tolist() == [len(c['selected'][:top_k])]
+            if c['selected']:
+                assert np.array_equal(rows[:, 1].astype(np.float32), np.asarray(c['scores'], np.float32)[c['selected'][:top_k]])
+
+
+@pytest.mark.parametrize('layer_cls,oracle_fn', [(DecodeDetections, orc.decode_layer), (DecodeDetectionsFast, orc.decode_layer_fast)])
+@pytest.mark.parametrize('cap,top_k', [(400, 200), (8, 200), (3, 50), (400, 20)])
+def test_keras_layer_contract_ssd300(layer_cls, oracle_fn, cap, top_k, ctx):
+    """SSD300-sized layer runs against the CPU restatement: the reference's defaults (cap 400, top_k 200), a
+    per-class cap that binds (8 and 3 boxes per class: `nms_max_output_size < top_k` also switches the kernel path),
+    and a small top_k."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 2, 96, bg_bias=7.0, hot=60)
+    layer = layer_cls(confidence_thresh=0.01, iou_threshold=0.45, top_k=top_k, nms_max_output_size=cap, img_height=300, img_width=300)
+    out = layer(y)
+    want = oracle_fn(y, 0.01, 0.45, top_k, cap, True, 300, 300, exp_mode='cr')
+    assert out.shape == (2, top_k, 6) and out.dtype == np.float32
+    assert np.array_equal(out, want)
+    if cap < top_k and layer_cls is DecodeDetections:
+        per_class = np.bincount(out[0, :, 0].astype(int), minlength=21)[1:]
+        assert per_class.max() == cap         # the cap really binds

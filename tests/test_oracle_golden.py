@@ -1,6 +1,7 @@
 """CPU tests: the oracle restatement against the committed golden vectors (which were produced
 by the real reference, see oracle/make_golden.py) and, where /root/reference is present, against
 the live reference itself."""
+import os
 import numpy as np
 import pytest
 
@@ -170,3 +171,19 @@ def test_ssd_loss_oracle_hand_case():
     # ratio 1: only the largest negative loss (-log 0.5)
     want1 = -np.log(.7) - np.log(.5) + 0.5 * (.01 + .04 + .09) + (1.6 - 0.5)
     assert abs(float(lo.compute_loss(yt, yp, neg_pos_ratio=1)[0]) - want1) < 1e-5
+
+
+def test_tf_nms_restatement_reproduces_tensorflows_published_unit_test_answers():
+    """a15 / SURVEY 8c: the Keras-layer contract rests on tf.image.non_max_suppression, a third-party op that
+    cannot be executed here.  Its own unit test's known answers (tests/golden/tf_nms_published.json, source cited
+    inside) pin the restatement's selection rule: IoU > threshold suppresses, descending score, flipped corner
+    order accepted, stop at max_output_size, identical boxes collapse to the first."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'tf_nms_published.json')) as fh:
+        vec = json.load(fh)
+    assert len(vec['cases']) >= 7
+    for c in vec['cases']:
+        b = np.array(c['boxes'], np.float32).reshape(-1, 4)
+        s = np.array(c['scores'], np.float32)
+        got = orc._tf_nms(b, s, c['max_output_size'], c['iou_threshold'])
+        assert got.tolist() == c['selected'], c['name']
