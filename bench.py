@@ -446,8 +446,8 @@ class DecodeWorkload(object):
             dt = time.perf_counter() - t
         else:
             out, dt = first, per
-        # oracle rows are [class, anchor, conf, coords] -> [anchor, class, conf, coords]
-        want = [np.zeros((0, 7)) if np.size(o) == 0 else np.concatenate([o[:, 1:2], o[:, 0:1], o[:, 2:]], axis=1) for o in out]
+        # oracle rows are [class, conf, coords, anchor] -> [anchor, class, conf, coords]
+        want = [np.zeros((0, 7)) if np.size(o) == 0 else np.concatenate([o[:, 6:7], o[:, :6]], axis=1) for o in out]
         base = {'value': n / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                 'sample': 'numpy oracle (restatement of the reference decode_detections), first %d image(s) of the '
                           'workload, 1 thread, %.2f s' % (n, dt)}

@@ -98,7 +98,7 @@ void ssdc_destroy(ssdc_ctx* ctx) {
         if (d.stream2) cudaStreamSynchronize(d.stream2);
         if (d.stream) cudaStreamSynchronize(d.stream);
         Buf* bufs[] = {&d.y_in, &d.ints, &d.keys, &d.boxes, &d.aux_class, &d.sort_scratch, &d.merge_scratch, &d.out_rows,
-                       &d.out_anchor, &d.out_count, &d.row_offset, &d.pad_rows, &d.pad_anchor, &d.gt, &d.gt_off, &d.partial, &d.matches,
+                       &d.out_anchor, &d.out_count, &d.row_offset, &d.hist, &d.pad_rows, &d.pad_anchor, &d.gt, &d.gt_off, &d.partial, &d.matches,
                        &d.enc_out, &d.enc_out2, &d.enc_idx, &d.enc_flags, &d.t0buf, &d.t1buf, &d.t2buf, &d.t3buf};
         for (Buf* b : bufs) b->release();
         for (int i = 0; i < DevCtx::H_RING; ++i) { d.h_ring[i].release(); if (d.h_ev[i]) cudaEventDestroy(d.h_ev[i]); }

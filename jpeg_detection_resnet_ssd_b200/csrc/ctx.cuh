@@ -95,6 +95,8 @@ struct DevCtx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // decode scratch
     Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
+    Buf hist;                        // image-sweep path: per-image 256-bin score histograms left by D1 (zero between decodes)
+    bool hist_clean = false;
     Buf pad_rows, pad_anchor;        // image-sweep path: (B, top_k, 6) float64 rows + anchor ids, as the sweep leaves them
     // small pinned staging areas for asynchronous H2D copies of per-call host data: a ring guarded by events, so a
     // call that only enqueues work never overwrites bytes an earlier call's copy has not read yet

@@ -43,7 +43,8 @@ template <typename T> struct alignas(16) SBox { T x0, y0, x1, y1; };
 
 struct DecodeArgs {
     int A, C, W, NS, tiles, tile_rows;
-    int dbg_null;                 // timing experiments only: consumers skip the tile (SSDC_D1_NULL)
+    int floor_target;             // image sweep: D1 keeps at least this many best candidates per image complete (score floor)
+    int have_hist;                // image sweep: D1 left per-image score histograms + floors (TMA kernel), else the sweep selects by radix passes
     int input_coords, log_wh, layer_assoc, ge;
     int do_nms, K, Kseg, always_sort;
     double iou_thr, sx, sy, d;
@@ -129,12 +130,149 @@ __device__ __forceinline__ void close_current(PendingKeys& pk, int* __restrict__
     pk.cur ^= 1; pk.n_cur = 0;
 }
 
+// ---------------------------------------------------------------------------
+// Speculative score floor of the image-sweep path.
+//
+// The sweep consumes the candidates of an image in descending score order and stops at top_k kept boxes, so of
+// the (possibly hundreds of thousands of) candidates that pass the confidence threshold only a prefix is ever
+// needed.  D1 therefore keeps, per CTA and image, a 256-bin histogram of the scores it has emitted so far
+// (bins of 1/16 octave, monotone in the key order) and raises a FLOOR to the highest bin edge that still has
+// `floor_target` emitted candidates at or above it: scores below the floor cannot be among the image's
+// `floor_target` best and are not emitted.  Every floor ever published is a valid lower bound of the
+// image's floor_target-th best score, so the set {score >= F} with F = the maximum published floor
+// (atomicMax, g_floor) is complete in the key list, and the flushed histograms are complete for the bins >= F.
+// The sweep trusts exactly that set; an image whose sweep runs dry inside it before top_k boxes are kept is
+// rescanned without a floor (exact fallback, sweep_kernel).  Typical inputs never reach floor_target
+// candidates per image, so nothing is dropped; dense inputs (low thresholds) shrink from 10^5 keys per image to
+// a few times floor_target.
+// ---------------------------------------------------------------------------
+constexpr int FL_BINS = 256;
+constexpr int FL_SHIFT = 19;                                         // ord32 >> 19: sign, exponent, 4 mantissa bits
+constexpr unsigned FL_BASE = (0xBF800000u >> FL_SHIFT) - (FL_BINS - 1);    // bin 255 <-> scores in [1.0 * 2^(-1/16).., ...)
+constexpr int FL_UPDATE = 256;                                       // histogram walk every FL_UPDATE emitted candidates
+__host__ __device__ __forceinline__ int floor_bin_of_ord(unsigned ord) {
+    const unsigned q = ord >> FL_SHIFT;
+    return q <= FL_BASE ? 0 : (q - FL_BASE > (unsigned)(FL_BINS - 1) ? FL_BINS - 1 : (int)(q - FL_BASE));
+}
+// smallest ord32 value of bin q (q >= 1)
+__host__ __device__ __forceinline__ unsigned floor_edge_ord(int q) { return (FL_BASE + (unsigned)q) << FL_SHIFT; }
+
+struct FloorSlot {
+    unsigned hist[FL_BINS];
+    float thr_excl;                // a candidate needs score > thr_excl (the confidence threshold, or just below the floor's edge)
+    int bin;                       // current floor bin (0: no floor)
+    unsigned since;                // candidates histogrammed so far (monotone; update trigger)
+    int image;                     // image the slot belongs to (-1: none)
+};
+
+// One warp re-derives the floor of its slot from the histogram (any snapshot of the monotone counters gives a valid bound).
+__device__ __forceinline__ void floor_update(FloorSlot* fs, int b, int target, float thr, int* __restrict__ g_floor) {
+    const int lane = threadIdx.x & 31;
+    volatile unsigned* h = fs->hist;
+    unsigned cnt[8];
+    int mine = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { cnt[q] = h[lane * 8 + q]; mine += (int)cnt[q]; }
+    int suffix = mine;                                   // candidates in this lane's bins and above
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += v;
+    }
+    const int above = suffix - mine;
+    const bool has = above < target && suffix >= target;
+    const unsigned hm = __ballot_sync(0xffffffffu, has);
+    if (!hm) return;                                     // fewer than `target` candidates so far
+    int qsel = 0;
+    if (has) {
+        int cum = above;
+        qsel = lane * 8;
+#pragma unroll
+        for (int q = 7; q >= 0; --q) {
+            cum += (int)cnt[q];
+            if (cum >= target) { qsel = lane * 8 + q; break; }
+        }
+    }
+    qsel = __shfl_sync(0xffffffffu, qsel, __ffs(hm) - 1);
+    if (lane == 0) {
+        const int seen = *reinterpret_cast<volatile int*>(&g_floor[b]);       // other CTAs working on the same image
+        int nb = qsel > seen ? qsel : seen;
+        if (nb > fs->bin) {
+            const float edge_excl = unord32(floor_edge_ord(nb) - 1u);          // largest float below the bin's lower edge
+            fs->bin = nb;
+            *reinterpret_cast<volatile float*>(&fs->thr_excl) = edge_excl > thr ? edge_excl : thr;
+            if (nb > seen) atomicMax(&g_floor[b], nb);
+        }
+    }
+}
+
+// Image-sweep variant of the tile filter (float32, per-class semantics, composite keys, one list per image).
+__device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst, int rows, int b, int a0,
+                                                   const DecodeArgs& g, float thr, int* __restrict__ seg_count,
+                                                   unsigned long long* __restrict__ gkeys, PendingKeys* pk,
+                                                   FloorSlot* fs, int* __restrict__ g_floor) {
+    const int W = g.W, NS = g.NS, A = g.A;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool valid = tid < rows;
+    const float* row = dst + (size_t)(valid ? tid : 0) * W;
+    const int a = a0 + tid;
+    const float t = fs ? *reinterpret_cast<volatile float*>(&fs->thr_excl) : thr;
+    int emitted = 0;
+    // ssd_output_decoder.py:207-209, 32 classes per pass
+    for (int c0 = 0; c0 < NS; c0 += 32) {
+        const int nc = min(32, NS - c0);
+        unsigned mask = 0;
+        for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] > t) << c;
+        if (!valid) mask = 0;
+        if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+        // keys carry the class: [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one slot reservation per warp
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        emitted += total;
+        unsigned long long* ck;
+        if (pk && total <= D1_PEND_HALF) {
+            if (pk->n_cur && (pk->b_cur != b || pk->n_cur + total > D1_PEND_HALF)) close_current(*pk, seg_count, gkeys, (size_t)NS * A);
+            ck = pk->buf + pk->cur * D1_PEND_HALF + pk->n_cur + (incl - cnt);
+        } else {
+            // a dense warp-tile (or no parking buffer): everything parked goes out first, then straight to global memory
+            if (pk) { close_current(*pk, seg_count, gkeys, (size_t)NS * A); retire_pending(*pk, gkeys, (size_t)NS * A); }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&seg_count[b], incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            ck = gkeys + (size_t)b * NS * A + base + (incl - cnt);
+        }
+        // (no box decode here: the sweep decodes the boxes of the candidates it actually visits from y_pred itself)
+        for (unsigned mm = mask; mm; mm &= mm - 1) {
+            const int c = __ffs(mm) - 1;
+            const unsigned ord = ord32(row[1 + c0 + c]);
+            *ck++ = ((unsigned long long)ord << 32) | ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
+                    (unsigned long long)(0xffffffu - (unsigned)a);
+            if (fs) atomicAdd(&fs->hist[floor_bin_of_ord(ord)], 1u);
+        }
+        if (pk && total <= D1_PEND_HALF) {
+            __syncwarp();
+            pk->n_cur += total; pk->b_cur = b;
+        }
+    }
+    if (fs && emitted) {
+        unsigned old = 0;
+        if (lane == 0) old = atomicAdd(&fs->since, (unsigned)emitted);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old / FL_UPDATE != (old + (unsigned)emitted) / FL_UPDATE) floor_update(fs, b, g.floor_target, thr, g_floor);
+    }
+}
+
 template <typename InT, bool FAST>
 __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int rows, int b, int a0,
                                              const DecodeArgs& g, InT thr, int* __restrict__ seg_count,
                                              typename KeyOf<InT>::type* __restrict__ keys,
-                                             SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class,
-                                             PendingKeys* pk = nullptr) {
+                                             SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
     typedef typename KeyOf<InT>::type KeyT;
     const int W = g.W, C = g.C, NS = g.NS, A = g.A;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -170,7 +308,6 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
 
     // ssd_output_decoder.py:207-209, 32 classes per pass
     bool any = false;
-    bool box_done = false;
     for (int c0 = 0; c0 < NS; c0 += 32) {
         const int nc = min(32, NS - c0);
         unsigned mask = 0;
@@ -183,52 +320,6 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
         const unsigned u = __reduce_or_sync(0xffffffffu, mask);
         if (!u) continue;
         any |= (mask != 0);
-        if (sizeof(InT) == 4 && g.sweep) {
-            // image sweep path: one candidate list per image, keys carry the class
-            // [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one atomic per warp
-            const int cnt = __popc(mask);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (pk) {
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(keys);
-                if (total <= D1_PEND_HALF) {
-                    if (pk->n_cur && (pk->b_cur != b || pk->n_cur + total > D1_PEND_HALF)) close_current(*pk, seg_count, gkeys, (size_t)NS * A);
-                    unsigned long long* ck = pk->buf + pk->cur * D1_PEND_HALF + pk->n_cur + (incl - cnt);
-                    for (unsigned mm = mask; mm; mm &= mm - 1) {
-                        const int c = __ffs(mm) - 1;
-                        *ck++ = ((unsigned long long)ord32((float)row[1 + c0 + c]) << 32) |
-                                ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
-                                (unsigned long long)(0xffffffu - (unsigned)a);
-                    }
-                    __syncwarp();
-                    pk->n_cur += total; pk->b_cur = b;
-                    box_done = true;
-                    continue;
-                }
-                // (a dense warp-tile: everything parked goes out first, then the direct path below)
-                close_current(*pk, seg_count, gkeys, (size_t)NS * A);
-                retire_pending(*pk, gkeys, (size_t)NS * A);
-            }
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&seg_count[b], incl);
-            // (no box decode here: the sweep decodes the boxes of the candidates it actually visits - a fraction of
-            // those that pass the threshold - from y_pred itself, with all lanes busy)
-            box_done = true;
-            base = __shfl_sync(0xffffffffu, base, 31);
-            unsigned long long* ck = reinterpret_cast<unsigned long long*>(keys) + (size_t)b * NS * A + base + (incl - cnt);
-            for (unsigned mm = mask; mm; mm &= mm - 1) {
-                const int c = __ffs(mm) - 1;
-                *ck++ = ((unsigned long long)ord32((float)row[1 + c0 + c]) << 32) |
-                        ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
-                        (unsigned long long)(0xffffffu - (unsigned)a);
-            }
-            continue;
-        }
         const int total = __reduce_add_sync(0xffffffffu, __popc(mask));
         if (total <= 2 * __popc(u)) {
             // sparse: about one candidate per class present in the warp, aggregation would not save
@@ -256,7 +347,7 @@ __device__ __forceinline__ void process_tile(const InT* __restrict__ dst, int ro
                 keys[((size_t)b * NS + c0 + c) * A + base + __popc(m & lt)] = KeyT::make(row[1 + c0 + c], (uint32_t)a);
         }
     }
-    if (any && !box_done) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
+    if (any) boxes[(size_t)b * A + a] = decode_box<InT>(row, C, g);
 }
 
 // Fallback loader: 128-bit LDG -> STS staging of one tile per CTA (any alignment).
@@ -303,7 +394,11 @@ decode_filter_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr,
         }
     }
     __syncthreads();
-    process_tile<InT, FAST>(dst, rows, b, a0, g, thr, seg_count, keys, boxes, aux_class);
+    if (sizeof(InT) == 4 && !FAST && g.sweep)
+        process_tile_sweep(reinterpret_cast<const float*>(dst), rows, b, a0, g, (float)thr, seg_count,
+                           reinterpret_cast<unsigned long long*>(keys), nullptr, nullptr, nullptr);
+    else
+        process_tile<InT, FAST>(dst, rows, b, a0, g, thr, seg_count, keys, boxes, aux_class);
 }
 
 // ---- TMA (cp.async.bulk) + mbarrier helpers ---------------------------------------------------
@@ -342,51 +437,105 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Requires 16-byte aligned tile spans (host checks; else the LDG kernel above runs).
 constexpr int D1_STAGES = 2;
 constexpr int D1_TMA_THREADS = D1_THREADS + 32;
+
+// Producer side of the score floor: adds a slot's histogram to the image's global one (complete for the bins at or
+// above the image's final floor) and re-arms the slot for image `b`.  Called by the whole producer warp when no
+// consumer can still be working on the slot's previous image.
+__device__ __forceinline__ void floor_slot_flush(FloorSlot* fs, unsigned* __restrict__ g_hist) {
+    const int lane = threadIdx.x & 31;
+    if (fs->image >= 0) {
+        unsigned* gh = g_hist + (size_t)fs->image * FL_BINS;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const unsigned v = fs->hist[lane * 8 + q];
+            if (v) atomicAdd(&gh[lane * 8 + q], v);
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void floor_slot_arm(FloorSlot* fs, int b, float thr, const int* __restrict__ g_floor) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) fs->hist[lane * 8 + q] = 0u;
+    if (lane == 0) {
+        const int seen = *reinterpret_cast<const volatile int*>(&g_floor[b]);      // a CTA that started the image earlier
+        const float edge_excl = seen > 0 ? unord32(floor_edge_ord(seen) - 1u) : thr;
+        fs->bin = seen;
+        fs->thr_excl = edge_excl > thr ? edge_excl : thr;
+        fs->since = 0u;
+        fs->image = b;
+    }
+    __syncwarp();
+}
+
 template <typename InT, bool FAST>
 __global__ void __launch_bounds__(D1_TMA_THREADS)
 decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int total_tiles,
                          int* __restrict__ seg_count, typename KeyOf<InT>::type* __restrict__ keys,
-                         SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class) {
+                         SBox<InT>* __restrict__ boxes, int* __restrict__ aux_class,
+                         int* __restrict__ g_floor, unsigned* __restrict__ g_hist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[D1_STAGES];
     __shared__ __align__(8) uint64_t empty[D1_STAGES];
+    __shared__ __align__(8) uint64_t done_bar;
     const int W = g.W, A = g.A;
     const size_t stage_bytes = (((size_t)g.tile_rows * W * sizeof(InT)) + 127) & ~(size_t)127;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr bool SWEEPABLE = (sizeof(InT) == 4) && !FAST;
+    const bool sweep = SWEEPABLE && g.sweep;
+    const bool floors = sweep && g.have_hist;             // score histograms + floor (needs >= D1_STAGES tiles per image, host-checked)
+    unsigned long long* pend_base = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)D1_STAGES * stage_bytes);
+    FloorSlot* slots = reinterpret_cast<FloorSlot*>(pend_base + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF);
     if (tid == 0) {
         for (int s = 0; s < D1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], D1_THREADS / 32); }
+        mbar_init(&done_bar, D1_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (floors) { slots[0].image = -1; slots[1].image = -1; }
     }
     __syncthreads();
 
     // every CTA owns a contiguous range of tiles (a warp then stays inside one image for many tiles, which is what
-    // lets it batch its slot reservations)
+    // lets it batch its slot reservations and lets the CTA keep ONE score histogram per image)
     const int per = total_tiles / (int)gridDim.x, extra = total_tiles - per * (int)gridDim.x;
     const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
     const int t_end = t_begin + per + ((int)blockIdx.x < extra ? 1 : 0);
     if (warp == D1_THREADS / 32) {
-        // ---- producer warp ----
-        if (lane == 0) {
-            int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
-            int it = 0;
-            for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
-                if (tile_id == g.tiles) { tile_id = 0; ++b; }
-                const int s = it % D1_STAGES;
-                if (it >= D1_STAGES) mbar_wait(&empty[s], (uint32_t)(((it / D1_STAGES) - 1) & 1));
+        // ---- producer warp (lane 0 issues the copies; the whole warp serves the floor slots) ----
+        int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
+        int it = 0, armed = -1;
+        for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
+            if (tile_id == g.tiles) { tile_id = 0; ++b; }
+            const int s = it % D1_STAGES;
+            if (it >= D1_STAGES) mbar_wait(&empty[s], (uint32_t)(((it / D1_STAGES) - 1) & 1));
+            if (floors && b != armed) {
+                // first tile of image b in this CTA.  Every consumer has released tile t - D1_STAGES, which lies in
+                // image b - 1 or later (an image has >= D1_STAGES tiles, host-checked), so nobody touches slot b & 1
+                // (image b - 2) any more; tile t itself cannot be consumed before its `full` barrier is armed below.
+                FloorSlot* fs = &slots[b & 1];
+                floor_slot_flush(fs, g_hist);
+                floor_slot_arm(fs, b, (float)thr, g_floor);
+                armed = b;
+            }
+            if (lane == 0) {
                 const int a0 = tile_id * g.tile_rows;
                 const int rows = min(g.tile_rows, A - a0);
                 const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
                 mbar_expect_tx(&full[s], bytes);
                 tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
             }
+            __syncwarp();
+        }
+        if (floors) {
+            mbar_wait(&done_bar, 0u);                         // all consumer warps are through their last tile
+            floor_slot_flush(&slots[0], g_hist);
+            floor_slot_flush(&slots[1], g_hist);
         }
         return;
     }
     // ---- consumer warps ----
     PendingKeys pend;
-    pend.buf = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)D1_STAGES * stage_bytes) + (size_t)warp * 2 * D1_PEND_HALF;
+    pend.buf = pend_base + (size_t)warp * 2 * D1_PEND_HALF;
     pend.cur = 0; pend.n_cur = 0; pend.b_cur = 0; pend.n_pend = 0; pend.b_pend = 0; pend.base_pend = 0;
-    const bool defer = (sizeof(InT) == 4) && !FAST && g.sweep;
     int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
@@ -395,16 +544,21 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
         mbar_wait(&full[s], (uint32_t)((it / D1_STAGES) & 1));
         const int a0 = tile_id * g.tile_rows;
         const int rows = min(g.tile_rows, A - a0);
-        if (g.dbg_null != 1)
-            process_tile<InT, FAST>(reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes), rows, b, a0, g, thr,
-                                    seg_count, keys, boxes, aux_class, defer ? &pend : nullptr);
+        const InT* tile = reinterpret_cast<const InT*>(smem_raw + (size_t)s * stage_bytes);
+        if (SWEEPABLE && sweep)
+            process_tile_sweep(reinterpret_cast<const float*>(tile), rows, b, a0, g, (float)thr, seg_count,
+                               reinterpret_cast<unsigned long long*>(keys), &pend, floors ? &slots[b & 1] : nullptr, g_floor);
+        else
+            process_tile<InT, FAST>(tile, rows, b, a0, g, thr, seg_count, keys, boxes, aux_class);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);             // this warp is done with stage s
     }
-    if (defer) {
+    if (sweep) {
         unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(keys);
         close_current(pend, seg_count, gkeys, (size_t)g.NS * A);
         retire_pending(pend, gkeys, (size_t)g.NS * A);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done_bar);
     }
 }
 
@@ -792,343 +946,445 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 }
 
 // ---------------------------------------------------------------------------
-// S: image sweep (decode_detections with a finite top_k; the hot configuration).
+// S: image sweep (decode_detections / DecodeDetections layer with a finite top_k; the hot configuration).
 //
 // Per-class greedy NMS followed by a cross-class top-k (ssd_output_decoder.py:205-221) equals one
 // sweep over ALL candidates of the image in descending (score, then class, then anchor) order in
 // which a candidate is only compared with kept boxes of its own class, stopped as soon as top_k
 // boxes are kept: later candidates have lower scores, so they can neither enter the top-k nor
 // influence a higher-scored decision.  Only the needed prefix of the candidate list is ever
-// selected (radix select), sorted and examined, independent of how many candidates the threshold
-// let through.  One CTA per image:
-//   select : 8-bit radix passes over the image's candidate keys pick a score threshold that yields
-//            the next <= 1024 best candidates; they are compacted into shared memory and sorted;
-//   sweep  : 32 candidates per step; the eight warps screen them against the kept boxes of the same
-//            class (lane <-> kept box, raw-corner disjointness), overlapping pairs are decided in
-//            batches (exact, division-free), warp 0 resolves the step and appends to the kept list.
+// selected, sorted and examined.  One CTA per image:
+//   select : D1 left a 256-bin score histogram of the image (exact for the bins at or above the image's score
+//            floor): one walk over it yields the bin edge above which the next ~top_k candidates lie - no pass
+//            over the keys.  (Radix passes over the keys remain as the fallback for degenerate score
+//            distributions - hundreds of candidates inside one 1/16-octave bin - and for the LDG loader.)
+//   compact: ONE pass over the image's keys moves that slice into shared memory;
+//   sort   : every warp sorts a run of the slice in registers (shuffle network), the runs are merged by rank
+//            (binary searches, one barrier) - no block-wide sorting network;
+//   decode : anchor-offset decode of the slice's boxes from their y_pred rows (prefetched to L2 during the sort);
+//   NMS    : panels of 128 candidates: thread <-> candidate computes (a) whether a kept box of its class
+//            suppresses it and (b) the bit mask of the earlier same-class candidates of the panel that would -
+//            per-class bit masks, raw-corner disjointness screening, exact division-free decisions (section 3.1
+//            of DESIGN.md); ONE warp then resolves the greedy order of the panel with bit operations.
+// An image whose trusted candidates (score >= floor) run out before top_k boxes are kept is rescanned from y_pred
+// without a floor by the same CTA and swept again (exact fallback of D1's speculative score floor).
 // ---------------------------------------------------------------------------
-// Threads per CTA (= per image) are a template parameter: 256 when all images fit one wave of 3 CTAs per
-// SM, else 128 (7 CTAs per SM: B = 1024 on 148 SMs is one wave).
 constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
-constexpr int SW_TARGET = 288;          // the selection aims at >= this many (and <= SW_CHUNK)
+constexpr int SW_TARGET = 288;          // later chunks aim at >= this many (and <= SW_CHUNK)
 constexpr int SW_KMAX = 256;            // largest top_k the sweep path handles
-constexpr int SW_QUEUE = 1024;          // per-warp pair queue (16-bit entries)
+constexpr int SW_PANEL = 128;           // candidates resolved per NMS panel
+constexpr int SW_PW = SW_PANEL / 32;
+constexpr int SW_KW = SW_KMAX / 32;
 
 __device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu - (unsigned)((k >> 24) & 0xffu)); }
 __device__ __forceinline__ unsigned ck_anchor(unsigned long long k) { return 0xffffffu - (unsigned)(k & 0xffffffu); }
 
+// Sorts kA[0..cn) (cn <= SW_CHUNK) descending into kB.  Runs of 32*R keys are sorted by one warp each in registers,
+// then every key finds its final position as the sum of its ranks in all runs (keys are unique).  Three barriers.
+template <int R>
+__device__ __forceinline__ void sort_runs(unsigned long long* kA) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* run = kA + (size_t)warp * 32 * R;
+    Key64 k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r].v = run[r * 32 + lane];
+    warp_sort_multi<Key64, R>(k, false);
+#pragma unroll
+    for (int r = 0; r < R; ++r) run[r * 32 + lane] = k[r].v;
+}
+template <int SW_THREADS>
+__device__ __forceinline__ void chunk_sort(unsigned long long* kA, unsigned long long* kB, int cn) {
+    constexpr int SW_WARPS = SW_THREADS / 32;
+    int S = 32 * SW_WARPS;
+    while (S < cn) S <<= 1;
+    const int L = S / SW_WARPS;                      // run length: 32, 64 or 128
+    for (int i = cn + threadIdx.x; i < S; i += SW_THREADS) kA[i] = 0ull;       // (0 sorts last; no real key is 0)
+    __syncthreads();
+    if (L == 32) sort_runs<1>(kA);
+    else if (L == 64) sort_runs<2>(kA);
+    else sort_runs<4>(kA);
+    __syncthreads();
+    for (int e = threadIdx.x; e < S; e += SW_THREADS) {
+        const unsigned long long key = kA[e];
+        if (key == 0ull) continue;
+        const int r = e / L;
+        int rank = e - r * L;
+#pragma unroll 1
+        for (int q = 0; q < SW_WARPS; ++q) {
+            if (q == r) continue;
+            const unsigned long long* other = kA + (size_t)q * L;
+            int lo = 0, hi = L;                          // number of keys of run q that come before `key`
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (other[mid] > key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        kB[rank] = key;
+    }
+    __syncthreads();
+}
+
 template <typename IouT, bool TF, int SW_THREADS>
-__global__ void __launch_bounds__(SW_THREADS, SW_THREADS == 256 ? 4 : 7)
-sweep_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
-             const float* __restrict__ y, DecodeArgs g,
+__global__ void __launch_bounds__(SW_THREADS, SW_THREADS == 256 ? 3 : 7)
+sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
+             const float* __restrict__ y, DecodeArgs g, float conf_thr,
+             int* __restrict__ g_floor, unsigned* __restrict__ g_hist,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
     constexpr int SW_WARPS = SW_THREADS / 32;
-    __shared__ unsigned long long ck[SW_CHUNK];                  // current chunk, sorted descending
+    extern __shared__ __align__(16) unsigned char sw_dyn[];      // cm[C][SW_PW] | km[C][SW_KW]
+    __shared__ unsigned long long kA[SW_CHUNK];                  // slice as compacted (unsorted), sort scratch
+    __shared__ unsigned long long kB[SW_CHUNK];                  // slice sorted descending
+    __shared__ SBox<float> cbox[SW_CHUNK];                       // raw corners of the slice's boxes
     __shared__ unsigned long long kkey[SW_KMAX];                 // kept keys in keep order
     __shared__ SBox<float> kraw[SW_KMAX];                        // their raw corners
     __shared__ unsigned char kcls[SW_KMAX];
-    __shared__ SBox<float> cbox[SW_CHUNK];                       // raw corners of the whole chunk (prefetched)
-    __shared__ SBox<float> craw[32];
-    __shared__ unsigned char ccls[32];
-    __shared__ unsigned cmask[256];                              // per class: candidates of the step
-    __shared__ unsigned sup[32];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned short queue[SW_WARPS][SW_QUEUE];
-    __shared__ unsigned s_dead, s_vm, s_cnt, s_screen_off;
-    __shared__ int s_nkept;
-    __shared__ unsigned long long s_tau, s_hi;
-    __shared__ int s_done;
+    __shared__ unsigned sup[SW_PW][SW_PANEL];                    // sup[w][i]: candidates 32w.. of the panel that suppress candidate i
+    __shared__ unsigned hist[FL_BINS];
+    __shared__ unsigned dead[SW_PW];
+    __shared__ unsigned s_cnt, s_screen_off;
+    __shared__ int s_nkept, s_done, s_bin;
+    __shared__ unsigned long long s_tau;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = g.K;
-    const int n = img_count[b];
-    const unsigned long long* gk = keys + (size_t)b * img_stride;
+    const int K = g.K, C = g.C;
+    unsigned* cm = reinterpret_cast<unsigned*>(sw_dyn);          // per class: candidates of the panel
+    unsigned* km = cm + (size_t)C * SW_PW;                        // per class: kept boxes (positions in keep order)
+    unsigned long long* gk = keys + (size_t)b * img_stride;
     const float* yb = y + (size_t)b * g.A * g.W;                 // this image's rows of y_pred
     const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
     const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
     const bool screen_ok = thr_ok && g.sx > 0.0 && g.sy > 0.0 && !TF;
     const unsigned lt = (1u << lane) - 1u;
 
-    if (tid == 0) { s_nkept = 0; s_hi = ~0ull; s_screen_off = 0; s_done = 0; }
-    for (int i = tid; i < 256; i += SW_THREADS) cmask[i] = 0;
+    int n = img_count[b];
+    int F = 0;                                                    // floor bin: keys of the bins >= F are complete
+    bool use_hist = g.have_hist != 0;
+    if (use_hist) {
+        F = g_floor[b];
+        for (int i = tid; i < FL_BINS; i += SW_THREADS) {
+            unsigned* gh = g_hist + (size_t)b * FL_BINS + i;
+            hist[i] = *gh;
+            *gh = 0u;                                            // (left clean for the next decode)
+        }
+    }
+    if (tid == 0) s_screen_off = 0;
     __syncthreads();
     if (n == 0) { if (tid == 0) out_count[b] = 0; return; }
 
-    // warp-local helper: lane's set bits of `mask` become queue entries (a << 5 | bit)
-    unsigned short* myq = queue[warp];
-    auto enqueue = [&](unsigned mask, unsigned a) -> int {
-        const int np = __popc(mask);
-        int start = np;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) {
+            // ---------------------------------------------------------------- exact fallback: rescan without a floor
+            for (int i = tid; i < FL_BINS; i += SW_THREADS) hist[i] = 0u;
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int a0 = 0; a0 < g.A; a0 += SW_THREADS) {
+                const int a = a0 + tid;
+                const float* row = yb + (size_t)(a < g.A ? a : 0) * g.W;
+                for (int c0 = 0; c0 < g.NS; c0 += 32) {
+                    const int nc = min(32, g.NS - c0);
+                    unsigned mask = 0;
+                    if (a < g.A)
+                        for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] > conf_thr) << c;
+                    if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+                    const int cnt = __popc(mask);
+                    int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, start, o);
-            if (lane >= o) start += v;
-        }
-        const int npairs = __shfl_sync(0xffffffffu, start, 31);
-        start -= np;
-        for (unsigned rem = mask; rem; rem &= rem - 1)
-            myq[start++] = (unsigned short)((a << 5) | (unsigned)(__ffs(rem) - 1));
-        __syncwarp();
-        return npairs;
-    };
-
-    int remaining = n;                      // candidates with key < s_hi
-    // First chunk: a little more than top_k candidates in the smallest power-of-two buffer that leaves the selection
-    // some slack - with little suppression that is all the sweep needs, and sorting 256 keys costs well under half of
-    // sorting 512 (K = 200: 0.062 -> 0.054 ms).  Later chunks (heavy suppression): SW_TARGET .. SW_CHUNK.
-    int target = K + max(K >> 3, 8), cap = 64;
-    while (cap < SW_CHUNK && target + 16 > cap) cap <<= 1;
-    if (target + 16 > cap || n > 8 * SW_CHUNK) { target = SW_TARGET; cap = SW_CHUNK; }      // (many candidates: another selection round would cost more than the bigger sort)
-    if (target < SW_TARGET / 8) target = SW_TARGET / 8;
-    while (true) {
-        // ------------------------------------------------------------ select the next chunk
-        const unsigned long long hi = s_hi;
-        unsigned long long tau = 0;
-        if (remaining > cap) {
-            unsigned long long prefix = 0;          // decided high bits of the threshold
-            unsigned long long pmask = 0;           // which bits are decided
-            int above = 0;                          // candidates above the bucket being refined
-            for (int shift = 56; shift >= 0; shift -= 8) {
-                for (int i = tid; i < 256; i += SW_THREADS) hist[i] = 0;
-                __syncthreads();
-                // (four independent loads in flight per thread: the pass is bound by the L2 round trip)
-                for (int i0 = tid; i0 < n; i0 += 8 * SW_THREADS) {
-                    unsigned long long k4[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * SW_THREADS;
-                        k4[u] = (i < n) ? gk[i] : ~0ull;                 // (~0: never below `hi`)
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (k4[u] < hi && (k4[u] & pmask) == prefix) atomicAdd(&hist[(unsigned)(k4[u] >> shift) & 255u], 1u);
+                    unsigned base = 0;
+                    if (lane == 31) base = atomicAdd(&s_cnt, (unsigned)incl);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    unsigned long long* out = gk + base + (incl - cnt);
+                    for (unsigned mm = mask; mm; mm &= mm - 1) {
+                        const int c = __ffs(mm) - 1;
+                        const unsigned ord = ord32(row[1 + c0 + c]);
+                        *out++ = ((unsigned long long)ord << 32) | ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
+                                 (unsigned long long)(0xffffffu - (unsigned)a);
+                        atomicAdd(&hist[floor_bin_of_ord(ord)], 1u);
+                    }
                 }
-                __syncthreads();
+            }
+            __syncthreads();
+            n = (int)s_cnt;
+            F = 0;
+            use_hist = true;
+        }
+        const unsigned long long lo_key = F ? ((unsigned long long)floor_edge_ord(F) << 32) : 0ull;   // trusted keys: >= lo_key
+        // per-class kept masks, kept count
+        for (int i = tid; i < C * SW_KW; i += SW_THREADS) km[i] = 0u;
+        if (tid == 0) s_nkept = 0;
+        // trusted candidates not yet consumed
+        int remaining = n;
+        if (use_hist) {
+            __syncthreads();
+            int part = 0;
+            for (int i = tid; i < FL_BINS; i += SW_THREADS) part += (i >= F) ? (int)hist[i] : 0;
+            part = __reduce_add_sync(0xffffffffu, part);
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            if (lane == 0) atomicAdd(&s_cnt, (unsigned)part);
+            __syncthreads();
+            remaining = (int)s_cnt;
+        }
+        __syncthreads();
+        unsigned long long hi = ~0ull;              // keys >= hi are consumed
+        int hi_bin = FL_BINS;                       // (histogram mode) bins >= hi_bin are consumed
+        // First slice: a little more than top_k candidates - with little suppression that is all the sweep needs.
+        int target = K + max(K >> 3, 8);
+        if (target > SW_TARGET) target = SW_TARGET;
+        while (remaining > 0) {
+            // ------------------------------------------------------------ select the next slice [tau, hi)
+            unsigned long long tau = lo_key;
+            int tau_bin = F;
+            if (use_hist) {
                 if (warp == 0) {
-                    // walk the 256 buckets from the top with one warp: lane l owns buckets [8l, 8l+8)
-                    int mine = 0;
+                    // walk the bins [F, hi_bin) from the top: lane l owns bins [8l, 8l+8)
+                    int cntq[8], mine = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) mine += (int)hist[lane * 8 + q];
-                    int suffix = mine;                       // sum over lanes >= this lane
+                    for (int q = 0; q < 8; ++q) {
+                        const int bin = lane * 8 + q;
+                        cntq[q] = (bin >= F && bin < hi_bin) ? (int)hist[bin] : 0;
+                        mine += cntq[q];
+                    }
+                    int suffix = mine;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int v = __shfl_down_sync(0xffffffffu, suffix, o);
                         if (lane + o < 32) suffix += v;
                     }
-                    const int cum_before = above + suffix - mine;     // candidates above this lane's buckets
-                    const bool has = (cum_before < target) && (cum_before + mine >= target);
+                    const int above = suffix - mine;
+                    const bool has = above < target && suffix >= target;
                     const unsigned hm = __ballot_sync(0xffffffffu, has);
-                    if (hm ? has : (lane == 0)) {            // (no lane: fewer than SW_TARGET left -> take everything)
-                        int cum = cum_before, dsel = lane * 8;
-                        for (int q = 7; q >= 0; --q) {
-                            const int h = (int)hist[lane * 8 + q];
-                            if (cum + h >= target || q == 0) { dsel = lane * 8 + q; break; }
-                            cum += h;
+                    if (hm ? has : (lane == 0)) {          // (no lane: fewer than `target` left -> everything down to F)
+                        int sel = F, cum = hm ? above : suffix;
+                        if (hm) {
+#pragma unroll
+                            for (int q = 7; q >= 0; --q) {
+                                cum += cntq[q];
+                                if (cum >= target) { sel = lane * 8 + q; break; }
+                            }
                         }
-                        // dsel: bucket in which the SW_TARGET-th best candidate lies
-                        s_cnt = (unsigned)cum;                        // strictly above the bucket
-                        s_tau = prefix | ((unsigned long long)dsel << shift);
-                        s_done = (cum + (int)hist[dsel] <= cap) || shift == 0;
+                        s_bin = sel;
+                        s_cnt = (unsigned)cum;              // candidates of the slice
                     }
                 }
                 __syncthreads();
-                prefix = s_tau;
-                pmask |= 0xffull << shift;
-                above = (int)s_cnt;
-                const int fin = s_done;
+                tau_bin = s_bin;
+                const int cnt = (int)s_cnt;
                 __syncthreads();
-                if (fin) break;
+                if (cnt > SW_CHUNK) use_hist = false;       // too many candidates inside one bin: refine by radix passes
+                else tau = tau_bin > 0 ? ((unsigned long long)floor_edge_ord(tau_bin) << 32) : 0ull;
+                if (tau < lo_key) tau = lo_key;
             }
-            tau = prefix;                               // lower edge of the selected bucket
-        }
-        if (g.dbg_null == 11) break;                  // (timing experiments: stop after the selection)
-        // compact {tau <= key < hi} into shared memory
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += 8 * SW_THREADS) {
-            unsigned long long k4[8];
+            if (!use_hist && remaining > SW_CHUNK) {
+                // 8-bit radix passes over the image's keys in [lo_key, hi): the bucket holding the target-th best
+                unsigned long long prefix = 0, pmask = 0;   // decided high bits of the threshold
+                int above = 0;                              // candidates above the bucket being refined
+                const int tgt = max(target, SW_TARGET);
+                for (int shift = 56; shift >= 0; shift -= 8) {
+                    unsigned* rh = &sup[0][0];              // 256 counters (sup is free during the selection)
+                    for (int i = tid; i < 256; i += SW_THREADS) rh[i] = 0u;
+                    __syncthreads();
+                    for (int i0 = tid; i0 < n; i0 += 8 * SW_THREADS) {
+                        unsigned long long k4[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * SW_THREADS + tid;
-                k4[u] = (i < n) ? gk[i] : ~0ull;                         // (~0: never below `hi`)
-            }
+                        for (int u = 0; u < 8; ++u) {
+                            const int i = i0 + u * SW_THREADS;
+                            k4[u] = (i < n) ? gk[i] : ~0ull;                 // (~0: never below `hi`)
+                        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const unsigned long long k = k4[u];
-                const bool take = k >= tau && k < hi;
-                const unsigned m = __ballot_sync(0xffffffffu, take);
-                if (m) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (take) ck[base + __popc(m & lt)] = k;
-                }
-            }
-        }
-        __syncthreads();
-        const int cn = (int)s_cnt;
-        if (g.dbg_null == 12) break;                  // (... after the compaction)
-        // the boxes of the chunk are decoded from y_pred after the sort: pull those rows towards L2 now, so that
-        // the DRAM round trip runs under the sort
-        for (int i = tid; i < cn; i += SW_THREADS) {
-            const float* rt = yb + (size_t)ck_anchor(ck[i]) * g.W + g.C;
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt));
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt + 11));
-        }
-        {
-            const int N = pow2_ceil(cn > 1 ? cn : 1);
-            for (int i = cn + tid; i < N; i += SW_THREADS) ck[i] = 0ull;
-            __syncthreads();
-            for (int k2 = 2; k2 <= N; k2 <<= 1) {
-                for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < (N >> 1); i += SW_THREADS) {
-                        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                        const int hi2 = lo | j;
-                        const unsigned long long a = ck[lo], c2 = ck[hi2];
-                        const bool desc = (lo & k2) == 0;
-                        if (desc ? (c2 > a) : (a > c2)) { ck[lo] = c2; ck[hi2] = a; }
+                        for (int u = 0; u < 8; ++u)
+                            if (k4[u] < hi && k4[u] >= lo_key && (k4[u] & pmask) == prefix) atomicAdd(&rh[(unsigned)(k4[u] >> shift) & 255u], 1u);
                     }
                     __syncthreads();
+                    if (warp == 0) {
+                        int mine = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) mine += (int)rh[lane * 8 + q];
+                        int suffix = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+                            if (lane + o < 32) suffix += v;
+                        }
+                        const int cum_before = above + suffix - mine;
+                        const bool has = (cum_before < tgt) && (cum_before + mine >= tgt);
+                        const unsigned hm = __ballot_sync(0xffffffffu, has);
+                        if (hm ? has : (lane == 0)) {
+                            int cum = cum_before, dsel = lane * 8;
+                            for (int q = 7; q >= 0; --q) {
+                                const int h = (int)rh[lane * 8 + q];
+                                if (cum + h >= tgt || q == 0) { dsel = lane * 8 + q; break; }
+                                cum += h;
+                            }
+                            s_cnt = (unsigned)cum;                        // strictly above the bucket
+                            s_tau = prefix | ((unsigned long long)dsel << shift);
+                            s_done = (cum + (int)rh[dsel] <= SW_CHUNK) || shift == 0;
+                        }
+                    }
+                    __syncthreads();
+                    prefix = s_tau;
+                    pmask |= 0xffull << shift;
+                    above = (int)s_cnt;
+                    const int fin = s_done;
+                    __syncthreads();
+                    if (fin) break;
+                }
+                tau = prefix > lo_key ? prefix : lo_key;    // lower edge of the selected bucket
+            }
+            // ------------------------------------------------------------ compact {tau <= key < hi} into shared memory
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int i0 = 0; i0 < n; i0 += 8 * SW_THREADS) {
+                unsigned long long k4[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * SW_THREADS + tid;
+                    k4[u] = (i < n) ? gk[i] : ~0ull;                         // (~0: never below `hi`)
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned long long k = k4[u];
+                    const bool take = k >= tau && k < hi;
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    if (m) {
+                        unsigned base = 0;
+                        if (lane == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const unsigned pos = base + __popc(m & lt);
+                        if (take && pos < SW_CHUNK) {
+                            kA[pos] = k;
+                            // the box is decoded from its y_pred row after the sort: pull the row towards L2 now
+                            const float* rt = yb + (size_t)ck_anchor(k) * g.W + g.C;
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(rt + 11));
+                        }
+                    }
                 }
             }
-        }
-
-        if (g.dbg_null == 13) break;                  // (... after the sort)
-        // ------------------------------------------------------------ sweep the chunk
-        // The boxes of the chunk are decoded from their y_pred rows two steps ahead of their use: the first 64
-        // here, the rest by warp 1 while warp 0 resolves a step - candidates the sweep never reaches (top_k kept
-        // before the chunk is exhausted) are never decoded, and the float64 `exp` runs in otherwise idle time.
-        const bool lazy = g.dbg_null != 20;
-        for (int i = tid; i < (lazy ? min(cn, 64) : cn); i += SW_THREADS) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
-        __syncthreads();
-        if (g.dbg_null == 14) break;                  // (... after the box decode)
-        // warp 0 owns the step state: lane <-> candidate.  `stage` publishes a step's candidates
-        unsigned long long key = 0;
-        bool valid = false;
-        SBox<float> me;
-        me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
-        int mycls = 0;
-        auto stage = [&](int t0) {
-            valid = t0 + lane < cn;
-            key = 0; mycls = 0;
-            me.x0 = me.y0 = 0.f; me.x1 = me.y1 = 1.f;
-            if (valid) {
-                key = ck[t0 + lane];
-                mycls = ck_cls(key);
-                me = cbox[t0 + lane];
-                atomicOr(&cmask[mycls], 1u << lane);
+            __syncthreads();
+            int cn = (int)s_cnt;
+            __syncthreads();
+            if (cn > SW_CHUNK) {
+                // (only possible when equal keys' multiplicity defeats the radix selection's last digit: cannot happen,
+                // keys are unique; kept as a guard so that shared memory is never overrun)
+                cn = SW_CHUNK;
             }
-            craw[lane] = me;
-            ccls[lane] = (unsigned char)mycls;
-            if (screen_ok && !s_screen_off) {
-                const Box<IouT> mb = scale_box<float, IouT>(me, sx, sy, d);
-                if (__any_sync(0xffffffffu, valid && !box_regular(mb))) { if (lane == 0) s_screen_off = 1; }
+            if (cn == 0) {
+                if (use_hist && tau_bin > F) { hi = tau; hi_bin = tau_bin; continue; }     // (empty bins above: keep walking)
+                break;
             }
-            const unsigned vmm = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) { s_vm = vmm; s_dead = 0; }
-        };
-        if (warp == 0 && cn > 0) stage(0);
-        __syncthreads();
-        for (int t0 = 0; t0 < cn; t0 += 32) {
-            int nkept = s_nkept;
-            if (nkept >= K) break;
+            // ------------------------------------------------------------ sort, decode the boxes
+            chunk_sort<SW_THREADS>(kA, kB, cn);
+            for (int i = tid; i < cn; i += SW_THREADS) {
+                const SBox<float> bx = decode_box<float>(yb + (size_t)ck_anchor(kB[i]) * g.W, g.C, g);
+                cbox[i] = bx;
+                if (screen_ok && !box_regular(scale_box<float, IouT>(bx, sx, sy, d))) s_screen_off = 1;
+            }
+            __syncthreads();
             const bool screen = screen_ok && !s_screen_off;
-            const unsigned vm = s_vm;
-
-            // (1) kept boxes of the same class: warp w takes kept boxes w*32.., lane <-> kept box
-            for (int k0 = warp * 32; k0 < nkept; k0 += SW_THREADS) {
-                const int k = k0 + lane;
-                unsigned mask = 0;
-                if (k < nkept) {
-                    unsigned cand = cmask[kcls[k]] & vm;
-                    if (screen) {
-                        const SBox<float> kr = kraw[k];
-                        for (unsigned rem = cand; rem; rem &= rem - 1) {
-                            const int c = __ffs(rem) - 1;
-                            if (raw_disjoint(craw[c], kr)) cand &= ~(1u << c);
+            // ------------------------------------------------------------ NMS panels
+            for (int p0 = 0; p0 < cn; p0 += SW_PANEL) {
+                const int P = min(SW_PANEL, cn - p0);
+                const int nkept = s_nkept;
+                if (nkept >= K) break;
+                for (int i = tid; i < C * SW_PW; i += SW_THREADS) cm[i] = 0u;
+                if (tid < SW_PW) dead[tid] = 0u;
+                __syncthreads();
+                for (int i = tid; i < P; i += SW_THREADS) atomicOr(&cm[(size_t)ck_cls(kB[p0 + i]) * SW_PW + (i >> 5)], 1u << (i & 31));
+                __syncthreads();
+                for (int i = tid; i < P; i += SW_THREADS) {
+                    const int cls = ck_cls(kB[p0 + i]);
+                    const SBox<float> me = cbox[p0 + i];
+                    // (a) kept boxes of the same class
+                    bool is_dead = false;
+                    const int kwords = (nkept + 31) >> 5;
+                    for (int w = 0; w < kwords && !is_dead; ++w) {
+                        for (unsigned rem = km[(size_t)cls * SW_KW + w]; rem; rem &= rem - 1) {
+                            const int k = (w << 5) + __ffs(rem) - 1;
+                            const SBox<float> kr = kraw[k];
+                            if (screen && raw_disjoint(me, kr)) continue;
+                            if (decide_pair<float, IouT, TF>(kr, me, sx, sy, d, thr, thr_ok)) { is_dead = true; break; }
                         }
                     }
-                    mask = cand;
-                }
-                const int npairs = enqueue(mask, (unsigned)lane);
-                for (int q0 = 0; q0 < npairs; q0 += 32) {
-                    bool sres = false;
-                    unsigned c = 0;
-                    if (q0 + lane < npairs) {
-                        const unsigned pr = myq[q0 + lane];
-                        c = pr & 31u;
-                        const int kk = k0 + (int)(pr >> 5);
-                        sres = decide_pair<float, IouT, TF>(kraw[kk], craw[c], sx, sy, d, thr, thr_ok);
+                    if (is_dead) { atomicOr(&dead[i >> 5], 1u << (i & 31)); continue; }
+                    // (b) earlier candidates of the panel with the same class
+                    const int wi = i >> 5;
+                    for (int w = 0; w <= wi; ++w) {
+                        unsigned rem = cm[(size_t)cls * SW_PW + w];
+                        if (w == wi) rem &= (1u << (i & 31)) - 1u;
+                        unsigned sw = 0;
+                        for (; rem; rem &= rem - 1) {
+                            const int bit = __ffs(rem) - 1;
+                            const SBox<float> ob = cbox[p0 + (w << 5) + bit];
+                            if (screen && raw_disjoint(me, ob)) continue;
+                            if (decide_pair<float, IouT, TF>(ob, me, sx, sy, d, thr, thr_ok)) sw |= 1u << bit;
+                        }
+                        sup[w][i] = sw;
                     }
-                    const unsigned dm = __reduce_or_sync(0xffffffffu, sres ? (1u << c) : 0u);
-                    if (dm && lane == 0) atomicOr(&s_dead, dm);
                 }
-                __syncwarp();
-            }
-            __syncthreads();
-
-            // (2)+(3) inside the step, warp 0
-            if (warp == 0) {
-                const unsigned dead = s_dead;
-                const bool alive = valid && !((dead >> lane) & 1u);
-                const unsigned am = vm & ~dead;
-                unsigned ovl = 0;
-                if (alive) {
-                    ovl = cmask[mycls] & am & lt;
-                    if (screen) {
-                        for (unsigned rem = ovl; rem; rem &= rem - 1) {
-                            const int j = __ffs(rem) - 1;
-                            if (raw_disjoint(me, craw[j])) ovl &= ~(1u << j);
+                __syncthreads();
+                if (warp == 0) {
+                    // greedy resolution of the panel, 32 candidates at a time
+                    unsigned keptw[SW_PW];
+#pragma unroll
+                    for (int w = 0; w < SW_PW; ++w) keptw[w] = 0u;
+                    int nk = nkept;
+#pragma unroll
+                    for (int gi = 0; gi < SW_PW; ++gi) {
+                        if (gi * 32 < P && nk < K) {
+                            const int i = gi * 32 + lane;
+                            const bool valid = i < P;
+                            bool alive = valid && !((dead[gi] >> lane) & 1u);
+                            unsigned mysup = 0;
+                            if (alive) {
+#pragma unroll
+                                for (int w = 0; w < SW_PW; ++w)
+                                    if (w < gi && (sup[w][i] & keptw[w])) alive = false;
+                                if (alive) mysup = sup[gi][i];
+                            }
+                            const unsigned am = __ballot_sync(0xffffffffu, alive);
+                            mysup &= am;
+                            const unsigned nz = __ballot_sync(0xffffffffu, mysup != 0u);
+                            unsigned keptm = am & ~nz;
+                            for (unsigned rem = nz; rem; rem &= rem - 1) {
+                                const int c = __ffs(rem) - 1;
+                                const unsigned sc = __shfl_sync(0xffffffffu, mysup, c);
+                                if (!(sc & keptm)) keptm |= 1u << c;
+                            }
+                            const int room = K - nk;
+                            const bool mine = ((keptm >> lane) & 1u) && (__popc(keptm & lt) < room);
+                            keptm = __ballot_sync(0xffffffffu, mine);
+                            if (mine) {
+                                const int pos = nk + __popc(keptm & lt);
+                                const unsigned long long key = kB[p0 + i];
+                                const int cls = ck_cls(key);
+                                kraw[pos] = cbox[p0 + i];
+                                kcls[pos] = (unsigned char)cls;
+                                kkey[pos] = key;
+                                atomicOr(&km[(size_t)cls * SW_KW + (pos >> 5)], 1u << (pos & 31));
+                            }
+                            keptw[gi] = keptm;
+                            nk += __popc(keptm);
                         }
                     }
+                    if (lane == 0) s_nkept = nk;
                 }
-                sup[lane] = 0;
-                const int npairs = enqueue(ovl, (unsigned)lane);
-                for (int q0 = 0; q0 < npairs; q0 += 32) {
-                    if (q0 + lane < npairs) {
-                        const unsigned pr = myq[q0 + lane];
-                        const unsigned c = pr >> 5, j = pr & 31u;
-                        if (decide_pair<float, IouT, TF>(craw[j], craw[c], sx, sy, d, thr, thr_ok))
-                            atomicOr(&sup[c], 1u << j);
-                    }
-                }
-                __syncwarp();
-                const unsigned mysup = sup[lane];
-                const unsigned nz = __ballot_sync(0xffffffffu, mysup != 0u) & am;
-                unsigned keptm = am & ~nz;
-                for (unsigned rem = nz; rem; rem &= rem - 1) {
-                    const int c = __ffs(rem) - 1;
-                    const unsigned sc = __shfl_sync(0xffffffffu, mysup, c);
-                    if (!(sc & keptm)) keptm |= 1u << c;
-                }
-                {
-                    const int room = K - nkept;
-                    const bool mine = ((keptm >> lane) & 1u) && (__popc(keptm & lt) < room);
-                    keptm = __ballot_sync(0xffffffffu, mine);
-                }
-                if ((keptm >> lane) & 1u) {
-                    const int pos = nkept + __popc(keptm & lt);
-                    kraw[pos] = me;
-                    kcls[pos] = (unsigned char)mycls;
-                    kkey[pos] = key;
-                }
-                if (valid) cmask[mycls] = 0;            // clear for the next step
-                const int nk2 = nkept + __popc(keptm);
-                if (lane == 0) s_nkept = nk2;
-                __syncwarp();
-                if (t0 + 32 < cn && nk2 < K) stage(t0 + 32);
-            } else if (warp == 1 && lazy) {
-                const int i = t0 + 64 + lane;           // the step after next
-                if (i < cn) cbox[i] = decode_box<float>(yb + (size_t)ck_anchor(ck[i]) * g.W, g.C, g);
+                __syncthreads();
             }
-            __syncthreads();
+            remaining -= cn;
+            if (s_nkept >= K) break;
+            hi = tau; hi_bin = tau_bin;
+            target = SW_TARGET;
+            if (tau <= lo_key) break;                   // every trusted candidate has been consumed
         }
-        const int nkept = s_nkept;
-        remaining -= cn;
-        if (nkept >= K || remaining <= 0 || cn == 0) break;
-        if (tid == 0) s_hi = tau;
-        target = SW_TARGET; cap = SW_CHUNK;
+        __syncthreads();
+        // ran dry inside the trusted set although D1 dropped candidates below the floor: do it again on all of them
+        if (!(s_nkept < K && F > 0)) break;
         __syncthreads();
     }
 
@@ -1513,43 +1769,52 @@ static float float_round_up(double x) {
 }
 
 struct IntLayout {
-    size_t seg_count, kept_count, lists, counters, total_ints;
+    size_t seg_count, floor, kept_count, lists, counters, total_ints;
 };
 static IntLayout int_layout(size_t nseg) {
     IntLayout L;
-    L.counters = 0;                       // 32 ints, zeroed together with seg_count
+    L.counters = 0;                       // 32 ints, zeroed together with seg_count and floor
     L.seg_count = 32;
-    L.kept_count = L.seg_count + nseg;
+    L.floor = L.seg_count + nseg;         // image sweep: per-image score floor bins (first B entries)
+    L.kept_count = L.floor + nseg;
     L.lists = L.kept_count + nseg;
     L.total_ints = L.lists + (size_t)NBINS * nseg;
     return L;
 }
 
+static bool d1_tma_ok(const void* y_dev, const DecodeArgs& g, size_t elem) {
+    const size_t row_bytes = (size_t)g.W * elem;
+    return (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (((size_t)g.A * row_bytes) % 16 == 0) &&
+           (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
+}
+
 template <typename InT>
 static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B, InT thr, bool fast,
-                     int* seg_count, typename KeyOf<InT>::type* keys, SBox<InT>* boxes, int* aux) {
+                     int* seg_count, typename KeyOf<InT>::type* keys, SBox<InT>* boxes, int* aux,
+                     int* g_floor = nullptr, unsigned* g_hist = nullptr) {
     cudaStream_t st = d->stream;
     constexpr int V = 16 / (int)sizeof(InT);
     LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
     const size_t row_bytes = (size_t)g.W * sizeof(InT);
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (((size_t)g.A * row_bytes) % 16 == 0) &&
-                        (((size_t)g.tile_rows * row_bytes) % 16 == 0) && ((((size_t)g.A % g.tile_rows) * row_bytes) % 16 == 0);
-    if (tma_ok) {
+    if (d1_tma_ok(y_dev, g, sizeof(InT))) {
         const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
-        const size_t smem = stage_bytes * D1_STAGES + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF * sizeof(unsigned long long);
+        const size_t smem = stage_bytes * D1_STAGES + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF * sizeof(unsigned long long) +
+                            2 * sizeof(FloorSlot);
         int ctas_per_sm = (int)((226 * 1024) / (smem + 1024 + 256));
         if (ctas_per_sm > 4) ctas_per_sm = 4;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
-        if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only)
+#ifdef SSDC_TIMING_KNOBS
+        if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only; not in release builds)
+#endif
         const long long total_tiles = (long long)B * g.tiles;
         long long grid = (long long)d->sm_count * ctas_per_sm;
         if (grid > total_tiles) grid = total_tiles;
         if (fast) {
             SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+            decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         } else {
             SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux);
+            decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         }
         SSDC_TRY(check_launch("decode_filter_tma_kernel"));
     } else {
@@ -1569,33 +1834,52 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
 
 // Image sweep path (decode_detections / DecodeDetections layer with a finite top_k, float32 input).
 template <typename InT, typename IouT, bool TF>
-static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B, InT thr) {
+static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, int64_t B, InT thr) {
     if (sizeof(InT) != 4) { set_error("internal: sweep path needs float32 input"); return SSDC_ERR_STATE; }
     typedef typename KeyOf<InT>::type KeyT;
     IntLayout L = int_layout((size_t)g.nseg);
     int* ints = d->ints.as<int>();
     int* img_count = ints + L.seg_count;            // one counter per image (first B entries)
+    int* g_floor = ints + L.floor;                  // one floor bin per image (zeroed with the counters)
     cudaStream_t st = d->stream;
-    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, false, img_count, d->keys.as<KeyT>(), d->boxes.as<SBox<InT>>(), nullptr));
+    // Score histograms + floor: only with the TMA loader, an image of >= D1_STAGES tiles and a positive target
+    int64_t target = ctx->opt[SSDC_OPT_FLOOR_TARGET];
+    if (target == 0) target = 4096;
+    if (target < 2LL * g.K + 64) target = 2LL * g.K + 64;            // (never tighter than what one sweep slice asks for)
+    if (target > 0x3fffffff) target = 0x3fffffff;
+    g.floor_target = (int)target;
+    g.have_hist = d1_tma_ok(y_dev, g, sizeof(InT)) && g.tiles >= D1_STAGES && ctx->opt[SSDC_OPT_FLOOR_TARGET] >= 0;
+    if (g.have_hist) {
+        const size_t hist_bytes = (size_t)B * FL_BINS * sizeof(unsigned);
+        if (hist_bytes > d->hist.cap) d->hist_clean = false;
+        SSDC_TRY(d->hist.ensure(hist_bytes));
+        if (!d->hist_clean) SSDC_CUDA(cudaMemsetAsync(d->hist.p, 0, d->hist.cap, st));
+        d->hist_clean = false;                      // (dirty until the sweep kernel, which leaves it zeroed, has been enqueued)
+    }
+    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, false, img_count, d->keys.as<KeyT>(), d->boxes.as<SBox<InT>>(), nullptr,
+                            g_floor, d->hist.as<unsigned>()));
     SSDC_TRY(d->pad_rows.ensure((size_t)B * g.K * 6 * sizeof(double)));
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
         LaunchScope ls(ctx, d, SSDC_K_NMS);
-        // one image per CTA: 256 threads while every image is resident at once (4 CTAs per SM), else 128 threads (7 per
-        // SM: B = 1024 on 148 SMs is one wave).  (On dense inputs the wide variant is much faster per image: SSD512 at
-        // conf 0.001, B = 512: 1.15 vs 2.0 ms.)
-        bool narrow = B > 4LL * d->sm_count;
-        if (const char* e = getenv("SSDC_SWEEP_THREADS")) narrow = atoi(e) == 128;      // (timing experiments only)
-        if (narrow)
-            sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, 0, st>>>(
-                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g,
-                d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
-        else
-            sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, 0, st>>>(
-                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g,
-                d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
+        // one image per CTA: 256 threads while every image of the batch is resident at once, else 128 threads (7 CTAs per
+        // SM: B = 1024 on 148 SMs is one wave)
+        const bool narrow = B > 3LL * d->sm_count;
+        const size_t dyn = (size_t)g.C * (SW_PW + SW_KW) * sizeof(unsigned);
+        if (narrow) {
+            SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, st>>>(
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
+                g_floor, d->hist.as<unsigned>(), d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
+        } else {
+            SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, dyn, st>>>(
+                d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
+                g_floor, d->hist.as<unsigned>(), d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
+        }
         SSDC_TRY(check_launch("sweep_kernel"));
     }
+    if (g.have_hist) d->hist_clean = true;
     // (the packed row offsets are only needed for the host copy: scan_counts_kernel runs at collect time)
     return SSDC_OK;
 }
@@ -1751,7 +2035,7 @@ static int run_emit(ssdc_ctx* ctx, DevCtx* d, const DecodeArgs& g, int64_t B) {
     return SSDC_OK;
 }
 
-static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* tf, int* cmp_rn) {
+static int build_args(const DecodeJob& job, bool no_sweep, DecodeArgs* out, int* iou_f32, int* tf, int* cmp_rn) {
     const ssdc_decode_params& p = job.p;
     DecodeArgs g;
     memset(&g, 0, sizeof(g));
@@ -1777,13 +2061,12 @@ static int build_args(const DecodeJob& job, DecodeArgs* out, int* iou_f32, int* 
     int rows = D1_THREADS;
     while (rows > 32 && ((size_t)rows * g.W + 4) * elem + 4096 > 100 * 1024) rows >>= 1;
     g.tile_rows = rows;
-    g.dbg_null = getenv("SSDC_D1_NULL") ? atoi(getenv("SSDC_D1_NULL")) : 0;
     g.tiles = (int)((job.A + rows - 1) / rows);
     // float32 input stays float32 end to end only where the reference never upcasts:
     // input_coords == 'corners' (ssd_output_decoder.py:186-190) and the Keras layers.
     // image sweep path: per-class semantics with a finite top_k that no per-class cap can undercut
     g.sweep = (job.dtype == SSDC_F32) && !fast && g.K > 0 && g.K <= SW_KMAX && job.C <= 256 && job.A < (1 << 24) &&
-              (!layer || p.nms_cap >= p.top_k) && getenv("SSDC_NO_SWEEP") == nullptr;
+              (!layer || p.nms_cap >= p.top_k) && !no_sweep;
     *iou_f32 = (job.dtype == SSDC_F32) && (layer || p.input_coords == SSDC_COORDS_CORNERS);
     *tf = layer;
     *cmp_rn = *iou_f32;
@@ -1799,7 +2082,7 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     job.b0 = b0; job.B = B; job.A = A; job.C = C; job.dtype = dtype; job.p = *p; job.emitted = false;
     if (B == 0) { job.valid = true; job.NS = 0; return SSDC_OK; }
     DecodeArgs g; int iou_f32, tf, cmp_rn;
-    SSDC_TRY(build_args(job, &g, &iou_f32, &tf, &cmp_rn));
+    SSDC_TRY(build_args(job, ctx->opt[SSDC_OPT_NO_SWEEP] != 0, &g, &iou_f32, &tf, &cmp_rn));
     job.NS = g.NS; job.iou_f32 = iou_f32;
     const size_t elem = (dtype == SSDC_F32) ? 4 : 8;
     const size_t in_bytes = (size_t)B * A * g.W * elem;
@@ -1872,7 +2155,7 @@ int decode_emit_all_dev(ssdc_ctx* ctx, DevCtx* d, int64_t total_rows) {
     if (job.emitted || job.B == 0) return SSDC_OK;
     SSDC_CUDA(cudaSetDevice(d->device));
     DecodeArgs g; int iou_f32, tf, cmp_rn;
-    SSDC_TRY(build_args(job, &g, &iou_f32, &tf, &cmp_rn));
+    SSDC_TRY(build_args(job, ctx->opt[SSDC_OPT_NO_SWEEP] != 0, &g, &iou_f32, &tf, &cmp_rn));
     job.out_capacity = total_rows;
     SSDC_TRY(d->out_rows.ensure((size_t)(total_rows + 1) * 6 * sizeof(double)));
     SSDC_TRY(d->out_anchor.ensure((size_t)(total_rows + 1) * sizeof(int)));

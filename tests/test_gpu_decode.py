@@ -341,3 +341,32 @@ def test_decode_many_classes(ctx, top_k):
     got, got_counts = product_rows7(rows, counts, idx)
     assert want_counts.sum() > 20 and int(want[:, 1].max()) > 40
     compare_rows(got, got_counts, want, want_counts, exact_coords=True)
+
+
+@pytest.mark.parametrize('layout,bias,thr,sigma', [('ssd300', 4.0, 0.01, 0.02), ('ssd300', 6.0, 0.01, 0.5), ('ssd512', 5.0, 0.001, 0.05),
+                                                   ('tiny', 0.5, 0.01, 0.02)])
+def test_score_floor_is_exact(layout, bias, thr, sigma, ctx):
+    """D1's speculative score floor never changes a result.  With the tightest floor the option allows, dense
+    candidates and boxes that sit on their anchors (neighbouring anchors overlap above the IoU threshold, so NMS
+    suppresses most candidates and the sweep needs far more of them than the floor kept complete) the sweep runs dry
+    inside the trusted set and takes the exact fallback (rescan without a floor); with the default floor it does not.
+    Both must equal the general per-class pipeline bit for bit, and so must a run with the floor switched off."""
+    enc = synth.make_encoder(SSDInputEncoder, layout)
+    kw = synth.layout_kwargs(layout)
+    C = kw['n_classes'] + 1
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 3, 78, bg_bias=bias, hot=40, offset_sigma=sigma)
+    args = (_lib.MODE_PER_CLASS, thr, 0.45)
+    tail = ('centroids', True, kw['img_height'], kw['img_width'], 'half')
+    for top_k in (200, 16):
+        ctx.set_option('no_sweep', 1)
+        try:
+            want = product_rows7(*_lib.run_decode(y, *args, top_k, *tail, ctx=ctx))
+        finally:
+            ctx.set_option('no_sweep', 0)
+        for target in (1, 0, -1):          # tightest floor, default, no floor
+            ctx.set_option('floor_target', target)
+            try:
+                got = product_rows7(*_lib.run_decode(y, *args, top_k, *tail, ctx=ctx))
+            finally:
+                ctx.set_option('floor_target', 0)
+            assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), (top_k, target)
