@@ -90,6 +90,8 @@ def parse_args():
     ap.add_argument('--no-cpu', action='store_true', help='skip cpu_baseline + parity gate (profiling runs only)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (profiling runs only)')
     ap.add_argument('--sustain-ms', type=float, default=200.0)
+    ap.add_argument('--floor-target', type=int, default=None, help='diagnosis: SSDC_OPT_FLOOR_TARGET of the context')
+    ap.add_argument('--sync-steps', action='store_true', help='diagnosis: synchronise after every warm-up step')
     return ap.parse_args()
 
 
@@ -457,7 +459,10 @@ class DecodeWorkload(object):
         got, gc = canonical7(self.device_results(n))
         wr, wc = canonical7(want)
         mx, exact = compare_rows7(got, gc, wr, wc, 'decode_detections, first %d images' % n)
-        return {'images': n, 'ok': True, 'rows': int(gc.sum()), 'indices_classes': 'exact', 'max_rel_err': mx, 'bit_identical': exact}
+        keys, floored, fallback = self.ctx.decode_stats()
+        return {'images': n, 'ok': True, 'rows': int(gc.sum()), 'indices_classes': 'exact', 'max_rel_err': mx, 'bit_identical': exact,
+                'whole_batch': {'candidates_emitted_per_image': round(keys / self.B, 1), 'images_with_score_floor': floored,
+                                'images_rescanned_without_floor': fallback}}
 
     def free(self):
         for d in self.d_y:
@@ -813,6 +818,8 @@ def main():
     from jpeg_detection_resnet_ssd_b200 import _lib, Context, set_context
     ctx = Context([local_rank])
     set_context(ctx)
+    if args.floor_target is not None:
+        ctx.set_option('floor_target', args.floor_target)
 
     batch, scaling = job_batch(args, cfg)
     if scaling == 'strong':
@@ -831,8 +838,11 @@ def main():
 
     # ---- device-resident timing: EXACTLY args.steps steps ---------------------------------------------
     warm = max(args.warmup, 3)
-    for _ in range(warm):
+    for i in range(warm):
         wl.step()
+        if args.sync_steps:
+            ctx.synchronize()
+            print('step %d ok' % i, file=sys.stderr, flush=True)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -86,7 +86,8 @@ int  ssdc_synchronize(ssdc_ctx* ctx);
 /* Per-context options (test / diagnosis switches; none changes a result).  Unknown option: SSDC_ERR_ARG. */
 #define SSDC_OPT_NO_SWEEP          0  /* 1: decode_detections runs the general per-class pipeline instead of the image sweep */
 #define SSDC_OPT_FLOOR_TARGET      1  /* image sweep: number of best candidates per image that D1 always keeps complete
-                                         (speculative score floor, exact fallback below it); 0 = default (4096)        */
+                                         (speculative score floor, exact fallback below it); 0 = default max(1024, 5 top_k),
+                                         < 0 = no floor                                                                 */
 #define SSDC_OPT_ENC_GENERAL       2  /* 1: encoder takes the general matching path                                    */
 #define SSDC_OPT_ENC_NO_OVERLAP    3  /* 1: encoder writes y_encoded with the fused write kernel (no template stream)  */
 #define SSDC_OPT_ENC_DENSE_PATCH   4  /* 1: encoder patches from the dense match array instead of the position list    */
@@ -183,6 +184,12 @@ int ssdc_decode_collect(ssdc_ctx* ctx, double* out_rows, int64_t capacity_rows,
  * the context's stream (`ssdc_synchronize`).  SSDC_ERR_STATE for other configurations (use `ssdc_decode_collect`). */
 int ssdc_decode_results_dev(ssdc_ctx* ctx, int dev_slot, const double** rows, const int32_t** anchors,
                             const int32_t** counts, int64_t* b0, int64_t* n_images, int32_t* top_k);
+
+/* Statistics of the last collected decode that took the image-sweep path (zeros otherwise), summed over the
+ * context's devices: out3[0] = candidate keys D1 emitted, out3[1] = images whose speculative score floor engaged
+ * (candidates below it were not emitted), out3[2] = images that ran dry inside the trusted set and took the exact
+ * fallback (rescan without a floor). */
+int ssdc_decode_stats(ssdc_ctx* ctx, int64_t* out3);
 
 /* submit + collect. */
 int ssdc_decode(ssdc_ctx* ctx, const void* y_pred, int dtype, int64_t B, int64_t A, int C,

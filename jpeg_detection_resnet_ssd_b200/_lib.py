@@ -80,6 +80,7 @@ SIGNATURES = {
     'ssdc_memcpy_d2h': (_i, [_vp, _i, _vp, _vp, C.c_uint64]),
     'ssdc_decode_submit': (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, C.POINTER(DecodeParams)]),
     'ssdc_decode_collect': (_i, [_vp, _vp, _i64, _vp, _vp, _pi64]),
+    'ssdc_decode_stats': (_i, [_vp, _pi64]),
     'ssdc_decode': (_i, [_vp, _vp, _i, _i64, _i64, _i, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _pi64]),
     'ssdc_decode_results_dev': (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pi64, _pi64, C.POINTER(C.c_int32)]),
     'ssdc_greedy_nms': (_i, [_vp, _vp, _vp, _i64, _d, _i, _i, _vp, _pi64]),
@@ -167,6 +168,13 @@ class Context(object):
         old = int(self.lib.ssdc_get_option(self.handle, OPTIONS[name]))
         check(self.lib.ssdc_set_option(self.handle, OPTIONS[name], int(value)))
         return old
+
+    def decode_stats(self):
+        """(keys emitted by D1, images with an engaged score floor, images that took the exact fallback) of the last
+        collected image-sweep decode."""
+        out = (C.c_int64 * 3)()
+        check(self.lib.ssdc_decode_stats(self.handle, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     # -- measurement helpers (bench.py / tests) --
     def synchronize(self):

@@ -350,6 +350,17 @@ int ssdc_decode_results_dev(ssdc_ctx* ctx, int dev_slot, const double** rows, co
     return SSDC_OK;
 }
 
+int ssdc_decode_stats(ssdc_ctx* ctx, int64_t* out3) {
+    if (!ctx || !out3) { set_error("ssdc_decode_stats: bad argument"); return SSDC_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    out3[0] = out3[1] = out3[2] = 0;
+    for (DevCtx& d : ctx->devs) {
+        if (!d.job.valid || !d.job.padded) continue;
+        out3[0] += d.job.stat_keys; out3[1] += d.job.stat_floored; out3[2] += d.job.stat_fallback;
+    }
+    return SSDC_OK;
+}
+
 int ssdc_decode(ssdc_ctx* ctx, const void* y_pred, int dtype, int64_t B, int64_t A, int C,
                 const ssdc_decode_params* p, double* out_rows, int64_t capacity_rows,
                 int32_t* out_counts, int32_t* out_anchor_idx, int64_t* total_rows) {

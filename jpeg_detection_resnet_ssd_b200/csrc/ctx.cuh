@@ -84,6 +84,7 @@ struct DecodeJob {
     bool scan_pending = false;      // image-sweep path: padded rows are on the device, the packed row offsets are not computed yet
     int64_t out_capacity = 0;       // rows the device out buffer can hold
     int iou_f32 = 0;
+    int64_t stat_keys = 0, stat_floored = 0, stat_fallback = 0;     // image sweep statistics, valid after the collect
 };
 
 struct DevCtx {

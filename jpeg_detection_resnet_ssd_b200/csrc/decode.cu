@@ -37,6 +37,8 @@ constexpr int NMS_WARPS = 4;
 constexpr int NBINS = 5;          // 0: nms list, 1..4: sort bins
 constexpr int CNT_LIST = 0;       // counters[0..4]  list sizes
 constexpr int CNT_CURSOR = 8;     // counters[8..12] work cursors
+constexpr int CNT_STAT_KEYS = 16, CNT_STAT_FLOORED = 17, CNT_STAT_FALLBACK = 18;      // image sweep statistics (ssdc_decode_stats)
+constexpr int CNT_STAT_ERR = 19;      // first violated invariant of the image-sweep kernels (0: none); the offending access is skipped
 constexpr int SORT_BYTES1 = 8 * 1024, SORT_BYTES2 = 32 * 1024, SORT_BYTES3 = 128 * 1024;   // shared-memory sort bins
 
 template <typename T> struct alignas(16) SBox { T x0, y0, x1, y1; };
@@ -116,7 +118,7 @@ __device__ __forceinline__ void retire_pending(PendingKeys& pk, unsigned long lo
     const int base = __shfl_sync(0xffffffffu, pk.base_pend, 31);
     unsigned long long* out = keys + (size_t)pk.b_pend * img_stride + base;
     const unsigned long long* src = pk.buf + (pk.cur ^ 1) * D1_PEND_HALF;
-    if (lane < pk.n_pend) out[lane] = src[lane];
+    if (lane < pk.n_pend && (size_t)(base + lane) < img_stride && base >= 0) out[lane] = src[lane];
     pk.n_pend = 0;
     __syncwarp();
 }
@@ -207,6 +209,11 @@ __device__ __forceinline__ void floor_update(FloorSlot* fs, int b, int target, f
 }
 
 // Image-sweep variant of the tile filter (float32, per-class semantics, composite keys, one list per image).
+// A warp-tile with many candidates (the floor has not caught up with the image yet: its first tiles) is filtered
+// twice: the candidates are counted into the histogram first, the floor is raised on the spot, and only what is
+// still above it is emitted - counted-but-dropped candidates lie below the floor, where the histogram is not
+// trusted anyway, and they are real candidates of the image, so the floor stays a valid bound.
+constexpr int D1_DENSE = 64;                  // candidates per warp-tile from which the floor is raised before emitting
 __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst, int rows, int b, int a0,
                                                    const DecodeArgs& g, float thr, int* __restrict__ seg_count,
                                                    unsigned long long* __restrict__ gkeys, PendingKeys* pk,
@@ -216,15 +223,38 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
     const bool valid = tid < rows;
     const float* row = dst + (size_t)(valid ? tid : 0) * W;
     const int a = a0 + tid;
-    const float t = fs ? *reinterpret_cast<volatile float*>(&fs->thr_excl) : thr;
-    int emitted = 0;
+    // (the slot's threshold is raised concurrently by other warps: one lane reads it, so that the whole warp filters -
+    // and branches - on the same value)
+    float t = fs ? __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0) : thr;
+    int counted = 0;                          // candidates added to the histogram by this call (warp-uniform)
     // ssd_output_decoder.py:207-209, 32 classes per pass
     for (int c0 = 0; c0 < NS; c0 += 32) {
         const int nc = min(32, NS - c0);
         unsigned mask = 0;
         for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] > t) << c;
         if (!valid) mask = 0;
-        if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+        int total = __reduce_add_sync(0xffffffffu, __popc(mask));
+        if (total == 0) continue;
+        bool in_hist = false;
+        if (fs && total >= D1_DENSE) {
+            for (unsigned mm = mask; mm; mm &= mm - 1)
+                atomicAdd(&fs->hist[floor_bin_of_ord(ord32(row[1 + c0 + __ffs(mm) - 1]))], 1u);
+            in_hist = true;
+            if (lane == 0) atomicAdd(&fs->since, (unsigned)total);
+            __syncwarp();
+            floor_update(fs, b, g.floor_target, thr, g_floor);
+            __syncwarp();
+            const float t2 = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0);
+            if (t2 > t) {
+                t = t2;
+                for (unsigned mm = mask; mm; mm &= mm - 1) {
+                    const int c = __ffs(mm) - 1;
+                    if (!(row[1 + c0 + c] > t)) mask &= ~(1u << c);
+                }
+                total = __reduce_add_sync(0xffffffffu, __popc(mask));
+                if (total == 0) continue;
+            }
+        }
         // keys carry the class: [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one slot reservation per warp
         const int cnt = __popc(mask);
         int incl = cnt;
@@ -233,10 +263,9 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        emitted += total;
         unsigned long long* ck;
-        if (pk && total <= D1_PEND_HALF) {
+        const bool park = pk && total <= D1_PEND_HALF;
+        if (park) {
             if (pk->n_cur && (pk->b_cur != b || pk->n_cur + total > D1_PEND_HALF)) close_current(*pk, seg_count, gkeys, (size_t)NS * A);
             ck = pk->buf + pk->cur * D1_PEND_HALF + pk->n_cur + (incl - cnt);
         } else {
@@ -246,6 +275,7 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
             if (lane == 31) base = atomicAdd(&seg_count[b], incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             ck = gkeys + (size_t)b * NS * A + base + (incl - cnt);
+            if (base < 0 || (size_t)base + (size_t)incl > (size_t)NS * A) mask = 0;      // (capacity guard: cannot happen, never write out of bounds)
         }
         // (no box decode here: the sweep decodes the boxes of the candidates it actually visits from y_pred itself)
         for (unsigned mm = mask; mm; mm &= mm - 1) {
@@ -253,18 +283,19 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
             const unsigned ord = ord32(row[1 + c0 + c]);
             *ck++ = ((unsigned long long)ord << 32) | ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
                     (unsigned long long)(0xffffffu - (unsigned)a);
-            if (fs) atomicAdd(&fs->hist[floor_bin_of_ord(ord)], 1u);
+            if (fs && !in_hist) atomicAdd(&fs->hist[floor_bin_of_ord(ord)], 1u);
         }
-        if (pk && total <= D1_PEND_HALF) {
+        if (park) {
             __syncwarp();
             pk->n_cur += total; pk->b_cur = b;
         }
+        if (!in_hist) counted += total;
     }
-    if (fs && emitted) {
+    if (fs && counted) {
         unsigned old = 0;
-        if (lane == 0) old = atomicAdd(&fs->since, (unsigned)emitted);
+        if (lane == 0) old = atomicAdd(&fs->since, (unsigned)counted);
         old = __shfl_sync(0xffffffffu, old, 0);
-        if (old / FL_UPDATE != (old + (unsigned)emitted) / FL_UPDATE) floor_update(fs, b, g.floor_target, thr, g_floor);
+        if (old / FL_UPDATE != (old + (unsigned)counted) / FL_UPDATE) floor_update(fs, b, g.floor_target, thr, g_floor);
     }
 }
 
@@ -712,6 +743,23 @@ __device__ __forceinline__ void warp_sort_multi(KeyT (&k)[R], bool by_anchor) {
     }
 }
 
+// Float32 evaluation of a pair of REGULAR boxes on their raw corners, valid when the union carries no border term
+// (d == 0: the IoU is invariant under the scaling by the image size).  The float32 IoU differs from the real number the
+// reference rounds (float64, relative error 1e-16) by < 2e-6 relative (a dozen roundings of 2^-24, no cancellation: the
+// union is at least the larger area), so outside a 2e-5 band around the threshold the float64 decision is known.
+// Returns 0: not suppressed, 1: suppressed, 2: inside the band (or out of the float32 range) - decide exactly.
+__device__ __forceinline__ int pair_f32(const SBox<float>& a, const SBox<float>& b, float thr_lo, float thr_hi) {
+    const float ix = fminf(a.x1, b.x1) - fmaxf(a.x0, b.x0);
+    const float iy = fminf(a.y1, b.y1) - fmaxf(a.y0, b.y0);
+    if (!(ix > 0.f) || !(iy > 0.f)) return 0;                        // disjoint: iou == +0 <= thr
+    const float inter = ix * iy;
+    const float uni = (a.x1 - a.x0) * (a.y1 - a.y0) + (b.x1 - b.x0) * (b.y1 - b.y0) - inter;
+    if (!(uni > 1e-30f && uni < 1e30f)) return 2;
+    if (inter < thr_lo * uni) return 0;
+    if (inter > thr_hi * uni) return 1;
+    return 2;
+}
+
 constexpr int NMS_SMEM_SORT = 128;              // segments of up to 128 candidates are sorted by the NMS warp itself
 constexpr int NMS_REG_MAX = NMS_SMEM_SORT;
 constexpr int NMS_QUEUE = 1024;                 // 16-bit pair entries: a full 32 x 32 block of pairs
@@ -1020,7 +1068,7 @@ __device__ __forceinline__ void chunk_sort(unsigned long long* kA, unsigned long
             }
             rank += lo;
         }
-        kB[rank] = key;
+        if (rank < S) kB[rank] = key;
     }
     __syncthreads();
 }
@@ -1029,9 +1077,8 @@ template <typename IouT, bool TF, int SW_THREADS>
 __global__ void __launch_bounds__(SW_THREADS, SW_THREADS == 256 ? 3 : 7)
 sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
              const float* __restrict__ y, DecodeArgs g, float conf_thr,
-             int* __restrict__ g_floor, unsigned* __restrict__ g_hist,
+             int* __restrict__ g_floor, unsigned* __restrict__ g_hist, int* __restrict__ stats,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
-    constexpr int SW_WARPS = SW_THREADS / 32;
     extern __shared__ __align__(16) unsigned char sw_dyn[];      // cm[C][SW_PW] | km[C][SW_KW]
     __shared__ unsigned long long kA[SW_CHUNK];                  // slice as compacted (unsorted), sort scratch
     __shared__ unsigned long long kB[SW_CHUNK];                  // slice sorted descending
@@ -1056,8 +1103,17 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
     const IouT sx = (IouT)g.sx, sy = (IouT)g.sy, d = (IouT)g.d, thr = (IouT)g.iou_thr;
     const bool thr_ok = thr > IouT(0) && thr < IouT(INFINITY);
     const bool screen_ok = thr_ok && g.sx > 0.0 && g.sy > 0.0 && !TF;
+    const bool f32_ok = screen_ok && g.d == 0.0 && g.iou_thr < 1e30;      // pair_f32 applies
+    const float thr_lo = (float)g.iou_thr * (1.0f - 2e-5f), thr_hi = (float)g.iou_thr * (1.0f + 2e-5f);
     const unsigned lt = (1u << lane) - 1u;
 
+    // the first reads of the kernel (count, histogram, keys) do not depend on one another: pull the key and histogram
+    // lines in while the count is on its way
+    {
+        const size_t lines = (img_stride * sizeof(unsigned long long) + 127) / 128;
+        for (size_t l = tid; l < lines && l < 2 * SW_CHUNK * sizeof(unsigned long long) / 128; l += SW_THREADS)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(gk) + l * 128));
+    }
     int n = img_count[b];
     int F = 0;                                                    // floor bin: keys of the bins >= F are complete
     bool use_hist = g.have_hist != 0;
@@ -1069,7 +1125,12 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
             *gh = 0u;                                            // (left clean for the next decode)
         }
     }
-    if (tid == 0) s_screen_off = 0;
+    if (tid == 0) {
+        s_screen_off = 0;
+        // statistics of the decode (ssdc_decode_stats): keys D1 emitted, images whose score floor engaged
+        atomicAdd(&stats[CNT_STAT_KEYS], n);
+        if (F > 0) atomicAdd(&stats[CNT_STAT_FLOORED], 1);
+    }
     __syncthreads();
     if (n == 0) { if (tid == 0) out_count[b] = 0; return; }
 
@@ -1077,7 +1138,7 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
         if (attempt == 1) {
             // ---------------------------------------------------------------- exact fallback: rescan without a floor
             for (int i = tid; i < FL_BINS; i += SW_THREADS) hist[i] = 0u;
-            if (tid == 0) s_cnt = 0;
+            if (tid == 0) { s_cnt = 0; atomicAdd(&stats[CNT_STAT_FALLBACK], 1); }
             __syncthreads();
             for (int a0 = 0; a0 < g.A; a0 += SW_THREADS) {
                 const int a = a0 + tid;
@@ -1281,12 +1342,18 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
             // ------------------------------------------------------------ sort, decode the boxes
             chunk_sort<SW_THREADS>(kA, kB, cn);
             for (int i = tid; i < cn; i += SW_THREADS) {
-                const SBox<float> bx = decode_box<float>(yb + (size_t)ck_anchor(kB[i]) * g.W, g.C, g);
+                unsigned anc = ck_anchor(kB[i]);
+                if (anc >= (unsigned)g.A || ck_cls(kB[i]) >= C || ck_cls(kB[i]) < 1) {       // invariant: every staged key is a real candidate
+                    atomicCAS(&stats[CNT_STAT_ERR], 0, 1 + (ck_cls(kB[i]) >= C || ck_cls(kB[i]) < 1));
+                    anc = 0; kB[i] = (kB[i] & 0xffffffff00000000ull) | (0xfeull << 24) | 0xffffffull;
+                }
+                const SBox<float> bx = decode_box<float>(yb + (size_t)anc * g.W, g.C, g);
                 cbox[i] = bx;
                 if (screen_ok && !box_regular(scale_box<float, IouT>(bx, sx, sy, d))) s_screen_off = 1;
             }
             __syncthreads();
             const bool screen = screen_ok && !s_screen_off;
+            const bool f32 = f32_ok && !s_screen_off;
             // ------------------------------------------------------------ NMS panels
             for (int p0 = 0; p0 < cn; p0 += SW_PANEL) {
                 const int P = min(SW_PANEL, cn - p0);
@@ -1307,7 +1374,11 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                         for (unsigned rem = km[(size_t)cls * SW_KW + w]; rem; rem &= rem - 1) {
                             const int k = (w << 5) + __ffs(rem) - 1;
                             const SBox<float> kr = kraw[k];
-                            if (screen && raw_disjoint(me, kr)) continue;
+                            if (f32) {
+                                const int r = pair_f32(me, kr, thr_lo, thr_hi);
+                                if (r == 0) continue;
+                                if (r == 1) { is_dead = true; break; }
+                            } else if (screen && raw_disjoint(me, kr)) continue;
                             if (decide_pair<float, IouT, TF>(kr, me, sx, sy, d, thr, thr_ok)) { is_dead = true; break; }
                         }
                     }
@@ -1321,7 +1392,11 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                         for (; rem; rem &= rem - 1) {
                             const int bit = __ffs(rem) - 1;
                             const SBox<float> ob = cbox[p0 + (w << 5) + bit];
-                            if (screen && raw_disjoint(me, ob)) continue;
+                            if (f32) {
+                                const int r = pair_f32(me, ob, thr_lo, thr_hi);
+                                if (r == 0) continue;
+                                if (r == 1) { sw |= 1u << bit; continue; }
+                            } else if (screen && raw_disjoint(me, ob)) continue;
                             if (decide_pair<float, IouT, TF>(ob, me, sx, sy, d, thr, thr_ok)) sw |= 1u << bit;
                         }
                         sup[w][i] = sw;
@@ -1844,7 +1919,9 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, i
     cudaStream_t st = d->stream;
     // Score histograms + floor: only with the TMA loader, an image of >= D1_STAGES tiles and a positive target
     int64_t target = ctx->opt[SSDC_OPT_FLOOR_TARGET];
-    if (target == 0) target = 4096;
+    // default: five times top_k, at least 1024 - the sweep reaches top_k kept boxes inside the trusted set unless NMS
+    // suppresses more than ~4 of 5 candidates in an image with more candidates than that (then: exact rescan)
+    if (target == 0) target = 5LL * g.K > 1024 ? 5LL * g.K : 1024;
     if (target < 2LL * g.K + 64) target = 2LL * g.K + 64;            // (never tighter than what one sweep slice asks for)
     if (target > 0x3fffffff) target = 0x3fffffff;
     g.floor_target = (int)target;
@@ -1870,12 +1947,12 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, i
             SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, st>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
-                g_floor, d->hist.as<unsigned>(), d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
+                g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         } else {
             SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, dyn, st>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
-                g_floor, d->hist.as<unsigned>(), d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
+                g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         }
         SSDC_TRY(check_launch("sweep_kernel"));
     }
@@ -2144,8 +2221,12 @@ int decode_finish_dev(ssdc_ctx* ctx, DevCtx* d, int64_t* total_rows) {
     }
     long long total = 0;
     SSDC_CUDA(cudaMemcpyAsync(&total, d->row_offset.as<long long>() + job.B, sizeof(long long), cudaMemcpyDeviceToHost, d->stream));
+    int st3[4] = {0, 0, 0, 0};
+    if (job.padded) SSDC_CUDA(cudaMemcpyAsync(st3, d->ints.as<int>() + CNT_STAT_KEYS, sizeof(st3), cudaMemcpyDeviceToHost, d->stream));
     SSDC_CUDA(cudaStreamSynchronize(d->stream));
     *total_rows = total;
+    job.stat_keys = st3[0]; job.stat_floored = st3[1]; job.stat_fallback = st3[2];
+    if (st3[3] != 0) { set_error("decode: internal invariant %d of the image sweep violated", st3[3]); return SSDC_ERR_STATE; }
     return SSDC_OK;
 }
 

@@ -355,6 +355,10 @@ def test_score_floor_is_exact(layout, bias, thr, sigma, ctx):
     kw = synth.layout_kwargs(layout)
     C = kw['n_classes'] + 1
     y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 3, 78, bg_bias=bias, hot=40, offset_sigma=sigma)
+    # (a floor only acts on the tiles a CTA filters AFTER it has seen enough candidates of the image: tile the three images
+    # to a batch in which every D1 CTA owns several tiles)
+    if layout != 'tiny':
+        y = np.ascontiguousarray(np.tile(y, (16 if layout == 'ssd300' else 8, 1, 1)))
     args = (_lib.MODE_PER_CLASS, thr, 0.45)
     tail = ('centroids', True, kw['img_height'], kw['img_width'], 'half')
     for top_k in (200, 16):
@@ -370,3 +374,39 @@ def test_score_floor_is_exact(layout, bias, thr, sigma, ctx):
             finally:
                 ctx.set_option('floor_target', 0)
             assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), (top_k, target)
+            keys, floored, fallback = ctx.decode_stats()
+            n_cand = int((y[:, :, 1:C] > thr).sum())
+            if target < 0:
+                assert (keys, floored, fallback) == (n_cand, 0, 0)
+            elif target == 1 and layout != 'tiny' and top_k == 200:
+                assert floored == y.shape[0] and keys < n_cand, (keys, n_cand)
+
+
+def test_score_floor_exact_fallback_under_heavy_suppression(ctx):
+    """One foreground class, every anchor a candidate, boxes sitting on their anchors: neighbouring anchors overlap
+    above the IoU threshold, NMS suppresses ~9 of 10 candidates, and top_k kept boxes need far more candidates than the
+    tightest floor keeps complete.  The sweep must notice that its trusted candidates ran out, rescan the image
+    without a floor and still equal the general pipeline bit for bit."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    A = 8732
+    rng = np.random.default_rng(5)
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 4, 79, bg_bias=9.0, hot=0, offset_sigma=0.01)
+    y[:, :, 1] = rng.uniform(0.02, 0.9, size=(4, A)).astype(np.float32)          # class 1 everywhere
+    y = np.ascontiguousarray(np.tile(y, (12, 1, 1)))
+    args = (_lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half')
+    ctx.set_option('no_sweep', 1)
+    try:
+        want = product_rows7(*_lib.run_decode(y, *args, ctx=ctx))
+    finally:
+        ctx.set_option('no_sweep', 0)
+    for target in (1, 0):
+        ctx.set_option('floor_target', target)
+        try:
+            got = product_rows7(*_lib.run_decode(y, *args, ctx=ctx))
+        finally:
+            ctx.set_option('floor_target', 0)
+        keys, floored, fallback = ctx.decode_stats()
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), target
+        assert floored == y.shape[0]
+        if target == 1:
+            assert fallback > 0, (keys, floored, fallback)
