@@ -1020,8 +1020,7 @@ nms_kernel(KeyT* __restrict__ keys, const int* __restrict__ seg_count, int* __re
 constexpr int SW_CHUNK = 512;           // candidates staged + sorted at a time
 constexpr int SW_TARGET = 288;          // later chunks aim at >= this many (and <= SW_CHUNK)
 constexpr int SW_KMAX = 256;            // largest top_k the sweep path handles
-constexpr int SW_PANEL = 128;           // candidates resolved per NMS panel
-constexpr int SW_PW = SW_PANEL / 32;
+// (candidates resolved per NMS panel = threads of the CTA: 128 or 256)
 constexpr int SW_KW = SW_KMAX / 32;
 
 __device__ __forceinline__ int ck_cls(unsigned long long k) { return (int)(0xffu - (unsigned)((k >> 24) & 0xffu)); }
@@ -1056,17 +1055,21 @@ __device__ __forceinline__ void chunk_sort(unsigned long long* kA, unsigned long
         const unsigned long long key = kA[e];
         if (key == 0ull) continue;
         const int r = e / L;
+        // number of keys of every other run that come before `key`: SW_WARPS - 1 independent binary searches, advanced
+        // in lock step so that their shared-memory reads overlap
+        int lo[SW_WARPS];
+#pragma unroll
+        for (int q = 0; q < SW_WARPS; ++q) lo[q] = 0;
+        for (int half = L >> 1; half > 0; half >>= 1) {
+#pragma unroll
+            for (int q = 0; q < SW_WARPS; ++q)
+                if (kA[q * L + lo[q] + half - 1] > key) lo[q] += half;          // (run q sorted descending, zero padded)
+        }
         int rank = e - r * L;
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < SW_WARPS; ++q) {
-            if (q == r) continue;
-            const unsigned long long* other = kA + (size_t)q * L;
-            int lo = 0, hi = L;                          // number of keys of run q that come before `key`
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (other[mid] > key) lo = mid + 1; else hi = mid;
-            }
-            rank += lo;
+            const int cntq = lo[q] + (kA[q * L + lo[q]] > key ? 1 : 0);
+            if (q != r) rank += cntq;
         }
         if (rank < S) kB[rank] = key;
     }
@@ -1079,6 +1082,8 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
              const float* __restrict__ y, DecodeArgs g, float conf_thr,
              int* __restrict__ g_floor, unsigned* __restrict__ g_hist, int* __restrict__ stats,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
+    constexpr int SW_PANEL = SW_THREADS;                         // candidates resolved per NMS panel: thread <-> candidate
+    constexpr int SW_PW = SW_PANEL / 32;
     extern __shared__ __align__(16) unsigned char sw_dyn[];      // cm[C][SW_PW] | km[C][SW_KW]
     __shared__ unsigned long long kA[SW_CHUNK];                  // slice as compacted (unsorted), sort scratch
     __shared__ unsigned long long kB[SW_CHUNK];                  // slice sorted descending
@@ -1107,13 +1112,25 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
     const float thr_lo = (float)g.iou_thr * (1.0f - 2e-5f), thr_hi = (float)g.iou_thr * (1.0f + 2e-5f);
     const unsigned lt = (1u << lane) - 1u;
 
-    // the first reads of the kernel (count, histogram, keys) do not depend on one another: pull the key and histogram
-    // lines in while the count is on its way
-    {
+    // the first reads of the kernel (count, floor, histogram, keys) do not depend on one another: the first 8 keys per
+    // thread are loaded now, speculatively (positions beyond the image's count hold stale keys and are masked when the
+    // count is known), so that the first compaction does not pay a second round trip
+    // (wide variant only: the narrow one runs at 7 CTAs per SM on a register budget that has no room for them and
+    // prefetches the lines to L2 instead)
+    constexpr bool PRELOAD = SW_THREADS == 256;
+    unsigned long long kpre[PRELOAD ? 8 : 1];
+    if (PRELOAD) {
+#pragma unroll
+        for (int u = 0; u < (PRELOAD ? 8 : 1); ++u) {
+            const size_t i = (size_t)u * SW_THREADS + tid;
+            kpre[u] = i < img_stride ? gk[i] : ~0ull;
+        }
+    } else {
         const size_t lines = (img_stride * sizeof(unsigned long long) + 127) / 128;
         for (size_t l = tid; l < lines && l < 2 * SW_CHUNK * sizeof(unsigned long long) / 128; l += SW_THREADS)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(gk) + l * 128));
     }
+    bool pre_valid = PRELOAD;
     int n = img_count[b];
     int F = 0;                                                    // floor bin: keys of the bins >= F are complete
     bool use_hist = g.have_hist != 0;
@@ -1302,10 +1319,15 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
             __syncthreads();
             for (int i0 = 0; i0 < n; i0 += 8 * SW_THREADS) {
                 unsigned long long k4[8];
+                if (PRELOAD && i0 == 0 && pre_valid) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u * SW_THREADS + tid;
-                    k4[u] = (i < n) ? gk[i] : ~0ull;                         // (~0: never below `hi`)
+                    for (int u = 0; u < 8; ++u) k4[u] = (u * SW_THREADS + tid < n) ? kpre[PRELOAD ? u : 0] : ~0ull;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * SW_THREADS + tid;
+                        k4[u] = (i < n) ? gk[i] : ~0ull;                     // (~0: never below `hi`)
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -1328,6 +1350,7 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                 }
             }
             __syncthreads();
+            pre_valid = false;                      // (the key list may be rewritten by the rescan; later slices reload)
             int cn = (int)s_cnt;
             __syncthreads();
             if (cn > SW_CHUNK) {
@@ -1942,7 +1965,7 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, i
         // one image per CTA: 256 threads while every image of the batch is resident at once, else 128 threads (7 CTAs per
         // SM: B = 1024 on 148 SMs is one wave)
         const bool narrow = B > 3LL * d->sm_count;
-        const size_t dyn = (size_t)g.C * (SW_PW + SW_KW) * sizeof(unsigned);
+        const size_t dyn = (size_t)g.C * ((narrow ? 128 : 256) / 32 + SW_KW) * sizeof(unsigned);
         if (narrow) {
             SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, st>>>(

@@ -391,8 +391,9 @@ def test_score_floor_exact_fallback_under_heavy_suppression(ctx):
     A = 8732
     rng = np.random.default_rng(5)
     y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 4, 79, bg_bias=9.0, hot=0, offset_sigma=0.01)
-    y[:, :, 1] = rng.uniform(0.02, 0.9, size=(4, A)).astype(np.float32)          # class 1 everywhere
-    y = np.ascontiguousarray(np.tile(y, (12, 1, 1)))
+    y[:, :, 1] = rng.uniform(0.02, 0.4, size=(4, A)).astype(np.float32)          # class 1 everywhere ...
+    y[:, :1216, 1] = rng.uniform(0.5, 0.9, size=(4, 1216)).astype(np.float32)     # ... its best candidates crowded into 8 rows of cells
+    y = np.ascontiguousarray(np.tile(y, (120, 1, 1)))        # (large enough that a D1 CTA filters whole images)
     args = (_lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half')
     ctx.set_option('no_sweep', 1)
     try:
