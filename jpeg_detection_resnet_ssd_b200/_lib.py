@@ -238,6 +238,67 @@ def _free_pinned(address):
         _lib.ssdc_host_free(C.c_void_p(address))
 
 
+class _PinnedPool(object):
+    """Recycled page-locked buffers for the large arrays the codec RETURNS (`y_encoded`: 2.3 MB per SSD300 image).
+
+    A fresh `np.empty` of that size costs a page fault per 4 KB on its first touch and makes the device-to-host copy a
+    staged pageable one (measured: 16 ms per batch of 32 where the copy itself takes 1.4 ms from pinned memory).  The
+    arrays handed out here are ordinary ndarrays over pinned memory; when the last view of one dies its buffer goes
+    back to the pool instead of to the driver, so a training loop that drops batch i before batch i + 2 arrives never
+    allocates again.  Bounded by SSDC_PINNED_POOL_GB (default 4) of outstanding + cached bytes; beyond that, or for
+    small arrays, plain numpy memory is returned."""
+    GRAIN = 1 << 21
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.free = {}           # size class -> [address]
+        self.bytes = 0           # outstanding + cached
+        self.limit = int(float(os.environ.get('SSDC_PINNED_POOL_GB', '4')) * 2 ** 30)
+
+    def empty(self, shape, dtype, min_bytes=1 << 22):
+        import weakref
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        n = count * dtype.itemsize
+        if n < min_bytes:
+            return np.empty(shape, dtype)
+        cls = (n + self.GRAIN - 1) // self.GRAIN * self.GRAIN
+        with self.lock:
+            lst = self.free.get(cls)
+            addr = lst.pop() if lst else None
+            if addr is None:
+                if self.bytes + cls > self.limit:
+                    return np.empty(shape, dtype)
+                self.bytes += cls
+        if addr is None:
+            p = C.c_void_p()
+            if load_library().ssdc_host_alloc(cls, C.byref(p)) != OK:
+                with self.lock:
+                    self.bytes -= cls
+                return np.empty(shape, dtype)
+            addr = p.value
+        buf = (C.c_char * n).from_address(addr)
+        weakref.finalize(buf, self._release, addr, cls)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _release(self, addr, cls):
+        with self.lock:
+            self.free.setdefault(cls, []).append(addr)
+
+    def trim(self):
+        """Returns every cached buffer to the driver."""
+        with self.lock:
+            addrs = [(a, c) for c, lst in self.free.items() for a in lst]
+            self.free = {}
+            self.bytes -= sum(c for _, c in addrs)
+        for a, _ in addrs:
+            if _lib is not None:
+                _lib.ssdc_host_free(C.c_void_p(a))
+
+
+pinned_pool = _PinnedPool()
+
+
 def default_devices():
     """SSDC_DEVICES="0,1,.." if set, else the torchrun LOCAL_RANK, else device 0."""
     env = os.environ.get('SSDC_DEVICES')

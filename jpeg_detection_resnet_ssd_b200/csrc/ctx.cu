@@ -102,6 +102,8 @@ void ssdc_destroy(ssdc_ctx* ctx) {
                        &d.enc_out, &d.enc_out2, &d.enc_idx, &d.enc_flags, &d.t0buf, &d.t1buf, &d.t2buf, &d.t3buf};
         for (Buf* b : bufs) b->release();
         for (int i = 0; i < DevCtx::H_RING; ++i) { d.h_ring[i].release(); if (d.h_ev[i]) cudaEventDestroy(d.h_ev[i]); }
+        for (int i = 0; i < DevCtx::FEED_RING; ++i) { d.feed_buf[i].release(); if (d.feed_ev[i]) cudaEventDestroy(d.feed_ev[i]); }
+        for (int i = 0; i < 8; ++i) if (d.chunk_ev[i]) cudaEventDestroy(d.chunk_ev[i]);
         if (d.t0) cudaEventDestroy(d.t0);
         if (d.t1) cudaEventDestroy(d.t1);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);

@@ -131,6 +131,12 @@ struct DevCtx {
         h_busy[s] = true;
         return SSDC_OK;
     }
+    // host input of a decode: chunked copies on stream2, pageable sources staged through pinned buffers
+    static constexpr int FEED_RING = 3;
+    PinnedBuf feed_buf[FEED_RING];
+    cudaEvent_t feed_ev[FEED_RING] = {nullptr, nullptr, nullptr};      // DMA out of the staging buffer finished
+    bool feed_busy[FEED_RING] = {false, false, false};
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // chunk landed on the device
     DecodeJob job;
     // encode scratch
     Buf gt, gt_off, partial, matches, enc_out, enc_out2, enc_idx, enc_flags;

@@ -29,6 +29,8 @@
 #include "ctx.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <sched.h>
+#include <thread>
 
 namespace ssdc {
 
@@ -1930,9 +1932,105 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     return SSDC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Host input.  The batch is copied in chunks of whole images on the copy stream (stream2) and D1 of a chunk is
+// enqueued on the main stream behind that chunk's copy: the filter of chunk k runs under the copy of chunk k + 1, the
+// rest of the pipeline starts when the last chunk has been filtered.  A pageable source (a plain numpy array - what
+// model.predict() returns) is staged through a ring of pinned buffers that a few host threads fill while the previous
+// chunk is on the wire; a pinned source is copied from directly.
+// ---------------------------------------------------------------------------
+struct HostFeed {
+    const char* src = nullptr;      // nullptr: the batch is already on the device
+    size_t img_bytes = 0;
+};
+
+static int host_threads(const ssdc_ctx* ctx) {
+    static int cached = 0;
+    if (!cached) {
+        int n = 0;
+        if (const char* e = getenv("SSDC_STAGE_THREADS")) n = atoi(e);
+        if (n <= 0) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            int cpus = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            n = cpus / 2;
+        }
+        cached = n < 1 ? 1 : (n > 8 ? 8 : n);
+    }
+    const int nd = (int)ctx->devs.size();
+    const int t = cached / (nd > 0 ? nd : 1);
+    return t < 1 ? 1 : t;
+}
+
+static void parallel_memcpy(char* dst, const char* src, size_t n, int threads) {
+    if (threads <= 1 || n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
+    const size_t per = ((n / threads) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; ++t) {
+        const size_t off = per * t;
+        if (off >= n) break;
+        const size_t len = n - off < per ? n - off : per;
+        th.emplace_back([=] { memcpy(dst + off, src + off, len); });
+    }
+    memcpy(dst, src, per < n ? per : n);
+    for (auto& x : th) x.join();
+}
+
+// Calls filter(b0, nb) for consecutive image ranges covering [0, B), each enqueued behind the arrival of its images.
+template <typename F>
+static int feed_chunks(ssdc_ctx* ctx, DevCtx* d, const HostFeed& feed, char* y_dev, int64_t B, F&& filter) {
+    if (!feed.src) return filter((int64_t)0, B);
+    int64_t chunk_mb = ctx->opt[SSDC_OPT_H2D_CHUNK_MB];
+    if (chunk_mb == 0) chunk_mb = 64;
+    const size_t total = (size_t)B * feed.img_bytes;
+    cudaPointerAttributes attr;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&attr, feed.src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    // images per chunk: whole images, chunk starts 16-byte aligned (the TMA loader needs it)
+    int64_t per = B;
+    if (chunk_mb > 0 && feed.img_bytes % 16 == 0) {
+        per = (int64_t)(((size_t)chunk_mb << 20) / feed.img_bytes);
+        if (per < 1) per = 1;
+        if (per * 2 > B && !pageable) per = B;                 // (fewer than two chunks: one copy)
+    }
+    if (per >= B && !pageable) {
+        SSDC_CUDA(cudaMemcpyAsync(y_dev, feed.src, total, cudaMemcpyHostToDevice, d->stream));
+        return filter((int64_t)0, B);
+    }
+    if (per > B) per = B;
+    const int threads = pageable ? host_threads(ctx) : 1;
+    cudaStream_t cs = d->stream2;
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += per, ++k) {
+        const int64_t nb = B - b0 < per ? B - b0 : per;
+        const size_t off = (size_t)b0 * feed.img_bytes, bytes = (size_t)nb * feed.img_bytes;
+        const char* from = feed.src + off;
+        if (pageable) {
+            const int s = k % DevCtx::FEED_RING;
+            if (d->feed_busy[s]) { SSDC_CUDA(cudaEventSynchronize(d->feed_ev[s])); d->feed_busy[s] = false; }
+            SSDC_TRY(d->feed_buf[s].ensure((size_t)per * feed.img_bytes));
+            parallel_memcpy(d->feed_buf[s].as<char>(), from, bytes, threads);
+            from = d->feed_buf[s].as<char>();
+            SSDC_CUDA(cudaMemcpyAsync(y_dev + off, from, bytes, cudaMemcpyHostToDevice, cs));
+            if (!d->feed_ev[s]) SSDC_CUDA(cudaEventCreateWithFlags(&d->feed_ev[s], cudaEventDisableTiming));
+            SSDC_CUDA(cudaEventRecord(d->feed_ev[s], cs));
+            d->feed_busy[s] = true;
+        } else {
+            SSDC_CUDA(cudaMemcpyAsync(y_dev + off, from, bytes, cudaMemcpyHostToDevice, cs));
+        }
+        cudaEvent_t& ev = d->chunk_ev[k % 8];
+        if (!ev) SSDC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SSDC_CUDA(cudaEventRecord(ev, cs));
+        SSDC_CUDA(cudaStreamWaitEvent(d->stream, ev, 0));
+        SSDC_TRY(filter(b0, nb));
+    }
+    return SSDC_OK;
+}
+
 // Image sweep path (decode_detections / DecodeDetections layer with a finite top_k, float32 input).
 template <typename InT, typename IouT, bool TF>
-static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, int64_t B, InT thr) {
+static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed& feed, DecodeArgs g, int64_t B, InT thr) {
     if (sizeof(InT) != 4) { set_error("internal: sweep path needs float32 input"); return SSDC_ERR_STATE; }
     typedef typename KeyOf<InT>::type KeyT;
     IntLayout L = int_layout((size_t)g.nseg);
@@ -1956,8 +2054,11 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, i
         if (!d->hist_clean) SSDC_CUDA(cudaMemsetAsync(d->hist.p, 0, d->hist.cap, st));
         d->hist_clean = false;                      // (dirty until the sweep kernel, which leaves it zeroed, has been enqueued)
     }
-    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, false, img_count, d->keys.as<KeyT>(), d->boxes.as<SBox<InT>>(), nullptr,
-                            g_floor, d->hist.as<unsigned>()));
+    SSDC_TRY(feed_chunks(ctx, d, feed, reinterpret_cast<char*>(const_cast<InT*>(y_dev)), B, [&](int64_t b0, int64_t nb) -> int {
+        return launch_d1<InT>(ctx, d, y_dev + (size_t)b0 * g.A * g.W, g, nb, thr, false, img_count + b0,
+                              d->keys.as<KeyT>() + (size_t)b0 * g.NS * g.A, d->boxes.as<SBox<InT>>(), nullptr,
+                              g_floor + b0, d->hist.as<unsigned>() + (size_t)b0 * FL_BINS);
+    }));
     SSDC_TRY(d->pad_rows.ensure((size_t)B * g.K * 6 * sizeof(double)));
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
@@ -1985,7 +2086,7 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, DecodeArgs g, i
 }
 
 template <typename InT, typename IouT, bool TF>
-static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B,
+static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed& feed, const DecodeArgs& g, int64_t B,
                         double conf_thresh, int cmp_f32_rn) {
     typedef typename KeyOf<InT>::type KeyT;
     const bool fast = (g.NS == 1);
@@ -2014,11 +2115,14 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const Decode
     }
 
     SSDC_CUDA(cudaMemsetAsync(ints, 0, (L.kept_count) * sizeof(int), st));
-    if (g.sweep) return run_sweep<InT, IouT, TF>(ctx, d, y_dev, g, B, thr);
+    if (g.sweep) return run_sweep<InT, IouT, TF>(ctx, d, y_dev, feed, g, B, thr);
     const int n1 = SORT_BYTES1 / (int)sizeof(KeyT), n2 = SORT_BYTES2 / (int)sizeof(KeyT), n3 = SORT_BYTES3 / (int)sizeof(KeyT);
 
     // D1
-    SSDC_TRY(launch_d1<InT>(ctx, d, y_dev, g, B, thr, fast, seg_count, keys, boxes, aux));
+    SSDC_TRY(feed_chunks(ctx, d, feed, reinterpret_cast<char*>(const_cast<InT*>(y_dev)), B, [&](int64_t b0, int64_t nb) -> int {
+        return launch_d1<InT>(ctx, d, y_dev + (size_t)b0 * g.A * g.W, g, nb, thr, fast, seg_count + (size_t)b0 * g.NS,
+                              keys + (size_t)b0 * g.NS * g.A, boxes + (size_t)b0 * g.A, aux ? aux + (size_t)b0 * g.A : nullptr);
+    }));
     // plan
     {
         LaunchScope ls(ctx, d, SSDC_K_PLAN);
@@ -2187,10 +2291,12 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     const size_t elem = (dtype == SSDC_F32) ? 4 : 8;
     const size_t in_bytes = (size_t)B * A * g.W * elem;
     const void* y_dev = y_pred;
+    HostFeed feed;
     if (!on_device) {
         SSDC_TRY(d->y_in.ensure(in_bytes));
-        SSDC_CUDA(cudaMemcpyAsync(d->y_in.p, y_pred, in_bytes, cudaMemcpyHostToDevice, d->stream));
         y_dev = d->y_in.p;
+        feed.src = reinterpret_cast<const char*>(y_pred);           // copied chunk by chunk, D1 behind every chunk (feed_chunks)
+        feed.img_bytes = (size_t)A * g.W * elem;
     }
     const size_t nseg = (size_t)g.nseg;
     IntLayout L = int_layout(nseg);
@@ -2203,11 +2309,11 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
 
     int r;
     if (dtype == SSDC_F32) {
-        if (!iou_f32) r = run_pipeline<float, double, false>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
-        else if (!tf) r = run_pipeline<float, float, false>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
-        else r = run_pipeline<float, float, true>(ctx, d, (const float*)y_dev, g, B, p->conf_thresh, cmp_rn);
+        if (!iou_f32) r = run_pipeline<float, double, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
+        else if (!tf) r = run_pipeline<float, float, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
+        else r = run_pipeline<float, float, true>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
     } else {
-        r = run_pipeline<double, double, false>(ctx, d, (const double*)y_dev, g, B, p->conf_thresh, cmp_rn);
+        r = run_pipeline<double, double, false>(ctx, d, (const double*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
     }
     SSDC_TRY(r);
 

@@ -215,8 +215,9 @@ class SSDInputEncoder(object):
         ctx, h = self._encoder()
         A = sum(int(b.shape[0] * b.shape[1] * b.shape[2]) for b in self.boxes_list)
         W = self.n_classes + 12
-        y = np.empty((B, A, W), dtype=np.float64)
-        y2 = np.empty((B, A, W), dtype=np.float64) if diagnostics else None
+        # (large results come from the recycled pinned pool: no first-touch page faults, direct DMA; see _lib._PinnedPool)
+        y = _lib.pinned_pool.empty((B, A, W), np.float64)
+        y2 = _lib.pinned_pool.empty((B, A, W), np.float64) if diagnostics else None
         mi = np.empty((B, A), dtype=np.int32) if return_matches else None
         rc = ctx.lib.ssdc_encode(h, _lib.ptr(gt), _lib.ptr(offs), B, 0, _lib.ptr(y), _lib.ptr(y2), _lib.ptr(mi))
         if rc == _lib.ERR_DEGENERATE:

@@ -402,12 +402,41 @@ def test_score_floor_exact_fallback_under_heavy_suppression(ctx):
         ctx.set_option('no_sweep', 0)
     for target in (1, 0):
         ctx.set_option('floor_target', target)
+        ctx.set_option('h2d_chunk_mb', -1)       # one copy, one D1 launch over the whole batch (chunks would shorten the CTAs' tile ranges)
         try:
             got = product_rows7(*_lib.run_decode(y, *args, ctx=ctx))
         finally:
             ctx.set_option('floor_target', 0)
+            ctx.set_option('h2d_chunk_mb', 0)
         keys, floored, fallback = ctx.decode_stats()
         assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), target
         assert floored == y.shape[0]
         if target == 1:
             assert fallback > 0, (keys, floored, fallback)
+
+
+@pytest.mark.parametrize('mode', ['per_class', 'fast'])
+def test_host_input_paths_agree(mode, ctx):
+    """A host batch reaches the device in chunks (D1 of a chunk behind its copy); pageable sources are staged through
+    pinned buffers by host threads.  One copy, small chunks, pinned and pageable memory: identical results."""
+    from jpeg_detection_resnet_ssd_b200 import pinned_empty
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    base = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, 21, 4, 80, bg_bias=7.0, hot=40)
+    y = np.ascontiguousarray(np.tile(base, (5, 1, 1)))[:19]         # 19 images (ragged last chunk), 21.9 MB
+    yp = pinned_empty(y.shape, y.dtype)
+    yp[...] = y
+    if mode == 'per_class':
+        args = (_lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half')
+    else:
+        args = (_lib.MODE_FAST, 0.3, 0.45, 'all', 'centroids', True, 300, 300, 'half')
+    ctx.set_option('h2d_chunk_mb', -1)
+    try:
+        want = _lib.run_decode(yp, *args, ctx=ctx)
+        for chunk_mb in (2, 5, 0):
+            ctx.set_option('h2d_chunk_mb', chunk_mb)
+            for src in (yp, y):
+                got = _lib.run_decode(src, *args, ctx=ctx)
+                for a, b in zip(got, want):
+                    assert np.array_equal(a, b), (chunk_mb, src is y)
+    finally:
+        ctx.set_option('h2d_chunk_mb', 0)
