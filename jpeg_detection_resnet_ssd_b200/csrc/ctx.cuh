@@ -140,6 +140,7 @@ struct DevCtx {
     DecodeJob job;
     // encode scratch
     Buf gt, gt_off, partial, matches, enc_out, enc_out2, enc_idx, enc_flags;
+    size_t cand_clean = 0;           // leading bytes of `matches` known to hold -1 (the sparse path's decision array between calls)
     // thin ops scratch
     Buf t0buf, t1buf, t2buf, t3buf;
 };

@@ -180,10 +180,8 @@ __global__ void permute_anchor_kernel(const int* __restrict__ perm, int S, const
     }
 }
 
-__global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, GtPrep* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double* r = gt + (size_t)i * 5;
+// One ground-truth row [class, xmin, ymin, xmax, ymax] -> normalised target-format box, corner form, screening data.
+__device__ __forceinline__ GtPrep make_gtprep(const double* __restrict__ r, const EncArgs& g) {
     double xmin = r[1], ymin = r[2], xmax = r[3], ymax = r[4];
     if (g.normalize) {          // ssd_input_encoder.py:339-341
         ymin = ymin / g.img_h; ymax = ymax / g.img_h;
@@ -210,7 +208,13 @@ __global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, 
     p.h_up = __fsub_ru(p.sf.w, p.sf.y);
     p.area_lo = __double2float_rd(p.box.area);
     p.pad = 0.f;
-    out[i] = p;
+    return p;
+}
+
+__global__ void gt_prep_kernel(const double* __restrict__ gt, int n, EncArgs g, GtPrep* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_gtprep(gt + (size_t)i * 5, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -914,13 +918,17 @@ constexpr float EL_FRAC = 0.7f;               // tau_r = EL_FRAC * (best IoU ins
 // valid; this choice keeps the lists short (a few dozen entries) and almost never dry.
 constexpr int ES_WARPS = 4;
 __global__ void __launch_bounds__(ES_WARPS * 32)
-seed_kernel(const GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restrict__ gtau) {
+seed_kernel(const double* __restrict__ gt_rows, EncArgs g, GtPrep* __restrict__ gtp, int n_gt, FastArgs f, float* __restrict__ gtau) {
     __shared__ int s_cut;
+    __shared__ GtPrep s_gp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x;
-    const GtPrep* gp = gtp + row;
+    // (the row's preparation happens here, not in a launch of its own: thread 0 derives it, everybody uses it, and it is
+    // left in global memory for the kernels that follow)
+    if (threadIdx.x == 0) { s_gp = make_gtprep(gt_rows + (size_t)row * 5, g); gtp[row] = s_gp; s_cut = 0; }
+    __syncthreads();
+    const GtPrep* gp = &s_gp;
     if (!gp->regular) { if (threadIdx.x == 0) gtau[row] = 0.f; return; }
-    if (threadIdx.x == 0) s_cut = 0;
     const int K = f.K;
     const float u0 = (lane < K) ? shape_bound(gp, f.cls[lane]) : -1.f;
     const float u1 = (lane + 32 < K) ? shape_bound(gp, f.cls[lane + 32]) : -1.f;
@@ -1446,13 +1454,15 @@ apply_kernel(const int* __restrict__ cand, const GtPrep* __restrict__ gtp, const
 
 // the same over the list of positions pair_kernel / greedy_kernel recorded (duplicates are harmless: same row, same values)
 __global__ void __launch_bounds__(128)
-apply_list_kernel(const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ cand,
+apply_list_kernel(const int* __restrict__ plist, const int* __restrict__ pcount, int* __restrict__ cand, int reset,
                   const GtPrep* __restrict__ gtp, const long long* __restrict__ gt_off,
                   const double* __restrict__ tail, EncArgs g, double* __restrict__ y, double* __restrict__ y2) {
     const int n = *pcount;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const long long i = plist[e];
-        const int c = cand[i];
+        // (a position can be listed twice - multi match and bipartite match of the same anchor: the first visitor takes
+        // the decision and, when the array is the library's own, leaves the entry clean for the next call)
+        const int c = reset ? atomicExch(&cand[i], -1) : cand[i];
         if (c != -1) apply_one(c, i, gtp, gt_off, tail, g, y, y2);
     }
 }
@@ -1546,27 +1556,40 @@ static bool build_shape_classes(const std::vector<Box<double>>& ab, ShapeClasses
     return true;
 }
 
-static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, int64_t* n_gt) {
+// The per-call host data of an encode reaches the device in ONE copy: [image offsets | ground-truth rows | zeros].  The
+// zeros initialise the small counters of the sparse path (list lengths per row, irregular-image flags, the patch
+// position counter), so no memset launch is needed; the prepared rows (GtPrep) live behind them.
+struct GtUpload {
+    int64_t n_gt = 0;
+    const long long* gt_off = nullptr;     // (B + 1) offsets relative to the shard
+    const double* rows = nullptr;          // n_gt x 5
+    int* zeros = nullptr;                  // n_gt + B + 1 ints, zero
+    GtPrep* gtp = nullptr;                 // n_gt prepared rows (written on the device)
+};
+static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, GtUpload* up) {
     const int64_t first = gt_offsets[b0], last = gt_offsets[b0 + B];
     const int64_t n = last - first;
-    *n_gt = n;
-    SSDC_TRY(d->gt_off.ensure((size_t)(B + 1) * sizeof(long long)));
-    // Offsets and rows are staged in ONE pinned area of the event-guarded ring: a call that only enqueues work
-    // (on_device outputs) may return before the copies ran, and neither the next call nor the caller's own reuse
-    // of `gt` may change the bytes they read.
+    up->n_gt = n;
+    // Staged in a pinned area of the event-guarded ring: a call that only enqueues work (on_device outputs) may return
+    // before the copy ran, and neither the next call nor the caller's own reuse of `gt` may change the bytes it reads.
     const size_t off_bytes = (((size_t)(B + 1) * sizeof(long long)) + 63) & ~(size_t)63;
-    const size_t gt_bytes = (size_t)n * 5 * sizeof(double);
+    const size_t gt_bytes = (((size_t)n * 5 * sizeof(double)) + 63) & ~(size_t)63;
+    const size_t z_bytes = (((size_t)(n + B + 1) * sizeof(int)) + 63) & ~(size_t)63;
+    const size_t copy_bytes = off_bytes + gt_bytes + z_bytes;
     void* hp = nullptr; int hs = 0;
-    SSDC_TRY(d->stage_acquire(off_bytes + gt_bytes, &hp, &hs));
-    long long* h = reinterpret_cast<long long*>(hp);
-    for (int64_t i = 0; i <= B; ++i) h[i] = gt_offsets[b0 + i] - first;
-    SSDC_CUDA(cudaMemcpyAsync(d->gt_off.p, h, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, d->stream));
-    if (n > 0) {
-        SSDC_TRY(d->gt.ensure((((size_t)n * 5 * sizeof(double) + 63) & ~(size_t)63) + (size_t)n * sizeof(GtPrep)));
-        char* hg = reinterpret_cast<char*>(hp) + off_bytes;
-        memcpy(hg, gt + first * 5, gt_bytes);
-        SSDC_CUDA(cudaMemcpyAsync(d->gt.p, hg, gt_bytes, cudaMemcpyHostToDevice, d->stream));
-    }
+    SSDC_TRY(d->stage_acquire(copy_bytes, &hp, &hs));
+    char* h = reinterpret_cast<char*>(hp);
+    long long* ho = reinterpret_cast<long long*>(h);
+    for (int64_t i = 0; i <= B; ++i) ho[i] = gt_offsets[b0 + i] - first;
+    if (n > 0) memcpy(h + off_bytes, gt + first * 5, (size_t)n * 5 * sizeof(double));
+    memset(h + off_bytes + gt_bytes, 0, z_bytes);
+    SSDC_TRY(d->gt.ensure(copy_bytes + (size_t)n * sizeof(GtPrep)));
+    char* dv = d->gt.as<char>();
+    SSDC_CUDA(cudaMemcpyAsync(dv, h, copy_bytes, cudaMemcpyHostToDevice, d->stream));
+    up->gt_off = reinterpret_cast<const long long*>(dv);
+    up->rows = reinterpret_cast<const double*>(dv + off_bytes);
+    up->zeros = reinterpret_cast<int*>(dv + off_bytes + gt_bytes);
+    up->gtp = n > 0 ? reinterpret_cast<GtPrep*>(dv + copy_bytes) : nullptr;
     return d->stage_done(hs, d->stream);
 }
 
@@ -1619,14 +1642,14 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         }
         if (ts != st) SSDC_CUDA(cudaEventRecord(d->ev_join, ts));
     }
-    int64_t n_gt = 0;
-    SSDC_TRY(upload_gt(d, gt, gt_offsets, b0, B, &n_gt));
-    const long long* gt_off = d->gt_off.as<long long>();
+    GtUpload up;
+    SSDC_TRY(upload_gt(d, gt, gt_offsets, b0, B, &up));
+    const int64_t n_gt = up.n_gt;
+    const long long* gt_off = up.gt_off;
     const Box<double>* abox = enc->dev[slot].anchor_box.as<Box<double>>();
     const double* tail = enc->dev[slot].anchor_tail.as<double>();
-    GtPrep* gtp = nullptr;
+    GtPrep* gtp = up.gtp;
     int* match = nullptr;
-    if (n_gt > 0) gtp = reinterpret_cast<GtPrep*>(d->gt.as<char>() + (((size_t)n_gt * 5 * sizeof(double) + 63) & ~(size_t)63));
 
     // ---- sparse path: shape classes + fused matching, then a patch of the few rows that differ from the template
     const double thr_min = g.multi ? (g.pos_thr < g.neg_thr ? g.pos_thr : g.neg_thr) : g.neg_thr;
@@ -1634,10 +1657,23 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
                         (!g.multi || g.pos_thr == g.pos_thr) && g.neg_thr == g.neg_thr && ctx->opt[SSDC_OPT_ENC_GENERAL] == 0;
     if (sparse) {
         const long long total = (long long)B * enc->A;
-        int* cand = midx_dev;
-        if (!cand) { SSDC_TRY(d->matches.ensure((size_t)total * sizeof(int))); cand = d->matches.as<int>(); }
-        if (n_gt > 0 || midx_dev) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
         const bool use_plist = total < 0x7fffffffLL && ctx->opt[SSDC_OPT_ENC_DENSE_PATCH] == 0;
+        int* cand = midx_dev;
+        if (cand) {
+            SSDC_CUDA(cudaMemsetAsync(cand, 0xff, (size_t)total * sizeof(int), st));
+        } else {
+            // The library's own decision array is kept all -1 BETWEEN calls: the patch kernel resets every entry it
+            // consumes (the position list names exactly the entries that were written), so the 4 bytes per anchor are
+            // only cleared once per allocation instead of once per call.
+            const size_t need = (size_t)total * sizeof(int);
+            if (need > d->matches.cap) d->cand_clean = 0;
+            SSDC_TRY(d->matches.ensure(need));
+            cand = d->matches.as<int>();
+            if (n_gt > 0) {
+                if (d->cand_clean < need) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, d->matches.cap, st));
+                d->cand_clean = 0;          // (dirty until the patch kernel of this call has been enqueued)
+            }
+        }
         int* plist = nullptr;
         int* pcount = nullptr;
         if (n_gt > 0) {
@@ -1657,8 +1693,6 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             size_t off = 0;
             auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
             const size_t o_mt = carve((size_t)n_gt * sizeof(int));
-            const size_t o_cnt = carve((size_t)n_gt * sizeof(int));
-            const size_t o_irr = carve((size_t)B * sizeof(int) + sizeof(int));       // + the position counter
             const size_t o_tau = carve((size_t)n_gt * sizeof(float));
             const size_t o_lv = carve((size_t)n_gt * EL_CAP * sizeof(double));
             const size_t o_li = carve((size_t)n_gt * EL_CAP * sizeof(int));
@@ -1666,22 +1700,16 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             SSDC_TRY(d->partial.ensure(off));
             char* base = d->partial.as<char>();
             match = reinterpret_cast<int*>(base + o_mt);
-            int* lcnt = reinterpret_cast<int*>(base + o_cnt);
-            int* img_irr = reinterpret_cast<int*>(base + o_irr);
+            int* lcnt = up.zeros;                       // list lengths, irregular flags and the position counter arrive
+            int* img_irr = up.zeros + n_gt;             // zeroed with the upload
             float* gtau = reinterpret_cast<float*>(base + o_tau);
             double* lval = reinterpret_cast<double*>(base + o_lv);
             int* lidx = reinterpret_cast<int*>(base + o_li);
             pcount = img_irr + B;
             plist = use_plist ? reinterpret_cast<int*>(base + o_pl) : nullptr;
-            SSDC_CUDA(cudaMemsetAsync(base + o_cnt, 0, (o_irr - o_cnt) + (size_t)(B + 1) * sizeof(int), st));     // lcnt, img_irr, pcount
             {
                 LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
-                gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
-                SSDC_TRY(check_launch("gt_prep_kernel"));
-            }
-            {
-                LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
-                seed_kernel<<<(unsigned)n_gt, ES_WARPS * 32, 0, st>>>(gtp, (int)n_gt, f, gtau);
+                seed_kernel<<<(unsigned)n_gt, ES_WARPS * 32, 0, st>>>(up.rows, g, gtp, (int)n_gt, f, gtau);
                 SSDC_TRY(check_launch("seed_kernel"));
             }
             {
@@ -1705,8 +1733,9 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         if (n_gt > 0 && dbg != 2) {
             LaunchScope ls(ctx, d, SSDC_K_ENC_PATCH);
             if (plist) {
-                apply_list_kernel<<<(unsigned)(d->sm_count * 8), 128, 0, st>>>(plist, pcount, cand, gtp, gt_off, tail, g, y_dev, y2_dev);
+                apply_list_kernel<<<(unsigned)(d->sm_count * 8), 128, 0, st>>>(plist, pcount, cand, midx_dev ? 0 : 1, gtp, gt_off, tail, g, y_dev, y2_dev);
                 SSDC_TRY(check_launch("apply_list_kernel"));
+                if (!midx_dev) d->cand_clean = d->matches.cap;
             } else {
                 long long blocks = (total + AP_WIN - 1) / AP_WIN;
                 if (blocks > (long long)d->sm_count * 8) blocks = (long long)d->sm_count * 8;
@@ -1736,7 +1765,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         SSDC_CUDA(cudaMemsetAsync(rowmax_bits, 0, (size_t)n_gt * sizeof(unsigned long long), st));
         {
             LaunchScope ls(ctx, d, SSDC_K_ENC_ROWBEST);
-            gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(d->gt.as<double>(), (int)n_gt, g, gtp);
+            gt_prep_kernel<<<(unsigned)((n_gt + 127) / 128), 128, 0, st>>>(up.rows, (int)n_gt, g, gtp);
             SSDC_TRY(check_launch("gt_prep_kernel"));
         }
         {
