@@ -91,6 +91,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg (profiling runs only)')
     ap.add_argument('--sustain-ms', type=float, default=200.0)
     ap.add_argument('--floor-target', type=int, default=None, help='diagnosis: SSDC_OPT_FLOOR_TARGET of the context')
+    ap.add_argument('--no-pipeline', type=int, default=None, help='diagnosis: SSDC_OPT_NO_PIPELINE of the context')
     ap.add_argument('--sync-steps', action='store_true', help='diagnosis: synchronise after every warm-up step')
     return ap.parse_args()
 
@@ -820,6 +821,8 @@ def main():
     set_context(ctx)
     if args.floor_target is not None:
         ctx.set_option('floor_target', args.floor_target)
+    if args.no_pipeline is not None:
+        ctx.set_option('no_pipeline', args.no_pipeline)
 
     batch, scaling = job_batch(args, cfg)
     if scaling == 'strong':

@@ -94,7 +94,9 @@ int  ssdc_synchronize(ssdc_ctx* ctx);
 #define SSDC_OPT_LOSS_NO_TMA       5  /* 1: loss uses the plain tile-copy loader                                       */
 #define SSDC_OPT_H2D_CHUNK_MB      6  /* host input of ssdc_decode_submit is copied in chunks of this many MiB, each chunk
                                          filtered (D1) while the next one is in flight; 0 = default (64), <0 = one copy */
-#define SSDC_OPT_COUNT             7
+#define SSDC_OPT_NO_PIPELINE       7  /* 1: the sweep of a device-resident image-sweep decode runs on the main stream (no overlap
+                                         with D1 of the next decode)                                                   */
+#define SSDC_OPT_COUNT             8
 int     ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value);
 int64_t ssdc_get_option(const ssdc_ctx* ctx, int option);
 

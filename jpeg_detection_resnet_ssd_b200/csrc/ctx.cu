@@ -75,9 +75,16 @@ int ssdc_init(const int* device_ids, int n_devices, ssdc_ctx** out) {
             ssdc_destroy(ctx); return SSDC_ERR_NODEVICE;
         }
         d.sm_count = prop.multiProcessorCount;
+        int prio_lo = 0, prio_hi = 0;
         if (cudaSetDevice(d.device) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&d.stream_nms, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_d1[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_d1[1], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_sweep[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_sweep[1], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreate(&d.t0) != cudaSuccess || cudaEventCreate(&d.t1) != cudaSuccess) {
@@ -96,7 +103,12 @@ void ssdc_destroy(ssdc_ctx* ctx) {
         if (d.device < 0) continue;
         cudaSetDevice(d.device);
         if (d.stream2) cudaStreamSynchronize(d.stream2);
+        if (d.stream_nms) cudaStreamSynchronize(d.stream_nms);
         if (d.stream) cudaStreamSynchronize(d.stream);
+        Buf* sb[] = {&d.shadow.ints, &d.shadow.keys, &d.shadow.hist, &d.shadow.pad_rows, &d.shadow.pad_anchor, &d.shadow.out_count};
+        for (Buf* b : sb) b->release();
+        for (int k = 0; k < 2; ++k) { if (d.ev_d1[k]) cudaEventDestroy(d.ev_d1[k]); if (d.ev_sweep[k]) cudaEventDestroy(d.ev_sweep[k]); }
+        if (d.stream_nms) cudaStreamDestroy(d.stream_nms);
         Buf* bufs[] = {&d.y_in, &d.ints, &d.keys, &d.boxes, &d.aux_class, &d.sort_scratch, &d.merge_scratch, &d.out_rows,
                        &d.out_anchor, &d.out_count, &d.row_offset, &d.hist, &d.pad_rows, &d.pad_anchor, &d.gt, &d.gt_off, &d.partial, &d.matches,
                        &d.enc_out, &d.enc_out2, &d.enc_idx, &d.enc_flags, &d.t0buf, &d.t1buf, &d.t2buf, &d.t3buf};
@@ -124,6 +136,8 @@ int ssdc_synchronize(ssdc_ctx* ctx) {
     for (DevCtx& d : ctx->devs) {
         SSDC_CUDA(cudaSetDevice(d.device));
         SSDC_CUDA(cudaStreamSynchronize(d.stream));
+        SSDC_CUDA(cudaStreamSynchronize(d.stream_nms));
+        d.sweep_pending[0] = d.sweep_pending[1] = false;
     }
     return SSDC_OK;
 }
@@ -189,6 +203,7 @@ int ssdc_timer_stop(ssdc_ctx* ctx, double* elapsed_ms) {
     double mx = 0.0;
     for (DevCtx& d : ctx->devs) {
         SSDC_CUDA(cudaSetDevice(d.device));
+        SSDC_TRY(d.wait_sweeps());                       // the span ends when the sweeps on the side stream have ended too
         SSDC_CUDA(cudaEventRecord(d.t1, d.stream));
     }
     for (DevCtx& d : ctx->devs) {

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <vector>
 #include <atomic>
+#include <utility>
 
 #include "../../include/ssdcodec.h"
 
@@ -98,6 +99,32 @@ struct DevCtx {
     Buf y_in, ints, keys, boxes, aux_class, sort_scratch, merge_scratch, out_rows, out_anchor, out_count, row_offset;
     Buf hist;                        // image-sweep path: per-image 256-bin score histograms left by D1 (zero between decodes)
     bool hist_clean = false;
+    // Pipelining of consecutive image-sweep decodes: the sweep of decode i runs on its own (lower priority) stream beside
+    // D1 of decode i + 1.  The scratch a decode owns from its D1 to its sweep (ints, keys, hist, pad_rows, pad_anchor,
+    // out_count, hist_clean above) exists twice; the members above are the bank of the LATEST decode, `shadow` holds the
+    // other one, and every image-sweep submit swaps them.
+    struct Bank { Buf ints, keys, hist, pad_rows, pad_anchor, out_count; bool hist_clean = false; } shadow;
+    int bank = 0;                                            // index of the current bank (events below)
+    cudaStream_t stream_nms = nullptr;
+    cudaEvent_t ev_d1[2] = {nullptr, nullptr};               // D1 of the bank's decode finished (recorded on `stream`)
+    cudaEvent_t ev_sweep[2] = {nullptr, nullptr};            // sweep of the bank's decode finished (recorded on `stream_nms`)
+    bool sweep_pending[2] = {false, false};
+    void swap_banks() {
+        std::swap(ints, shadow.ints); std::swap(keys, shadow.keys); std::swap(hist, shadow.hist);
+        std::swap(pad_rows, shadow.pad_rows); std::swap(pad_anchor, shadow.pad_anchor); std::swap(out_count, shadow.out_count);
+        std::swap(hist_clean, shadow.hist_clean);
+        bank ^= 1;
+    }
+    // makes `stream` wait for the sweeps still in flight on `stream_nms` (bank b, or both for b < 0)
+    int wait_sweeps(int b = -1) {
+        for (int k = 0; k < 2; ++k) {
+            if ((b >= 0 && k != b) || !sweep_pending[k]) continue;
+            cudaError_t e = cudaStreamWaitEvent(stream, ev_sweep[k], 0);
+            if (e != cudaSuccess) { set_error("cudaStreamWaitEvent(sweep) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
+            sweep_pending[k] = false;
+        }
+        return SSDC_OK;
+    }
     Buf pad_rows, pad_anchor;        // image-sweep path: (B, top_k, 6) float64 rows + anchor ids, as the sweep leaves them
     // small pinned staging areas for asynchronous H2D copies of per-call host data: a ring guarded by events, so a
     // call that only enqueues work never overwrites bytes an earlier call's copy has not read yet

@@ -1891,7 +1891,7 @@ static bool d1_tma_ok(const void* y_dev, const DecodeArgs& g, size_t elem) {
 template <typename InT>
 static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArgs& g, int64_t B, InT thr, bool fast,
                      int* seg_count, typename KeyOf<InT>::type* keys, SBox<InT>* boxes, int* aux,
-                     int* g_floor = nullptr, unsigned* g_hist = nullptr) {
+                     int* g_floor = nullptr, unsigned* g_hist = nullptr, int max_ctas_per_sm = 4) {
     cudaStream_t st = d->stream;
     constexpr int V = 16 / (int)sizeof(InT);
     LaunchScope ls(ctx, d, SSDC_K_DECODE_FILTER);
@@ -1901,7 +1901,7 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         const size_t smem = stage_bytes * D1_STAGES + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF * sizeof(unsigned long long) +
                             2 * sizeof(FloorSlot);
         int ctas_per_sm = (int)((226 * 1024) / (smem + 1024 + 256));
-        if (ctas_per_sm > 4) ctas_per_sm = 4;
+        if (ctas_per_sm > max_ctas_per_sm) ctas_per_sm = max_ctas_per_sm;
         if (ctas_per_sm < 1) ctas_per_sm = 1;
 #ifdef SSDC_TIMING_KNOBS
         if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only; not in release builds)
@@ -2030,7 +2030,7 @@ static int feed_chunks(ssdc_ctx* ctx, DevCtx* d, const HostFeed& feed, char* y_d
 
 // Image sweep path (decode_detections / DecodeDetections layer with a finite top_k, float32 input).
 template <typename InT, typename IouT, bool TF>
-static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed& feed, DecodeArgs g, int64_t B, InT thr) {
+static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed& feed, DecodeArgs g, int64_t B, InT thr, bool pipe) {
     if (sizeof(InT) != 4) { set_error("internal: sweep path needs float32 input"); return SSDC_ERR_STATE; }
     typedef typename KeyOf<InT>::type KeyT;
     IntLayout L = int_layout((size_t)g.nseg);
@@ -2059,6 +2059,16 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed&
                               d->keys.as<KeyT>() + (size_t)b0 * g.NS * g.A, d->boxes.as<SBox<InT>>(), nullptr,
                               g_floor + b0, d->hist.as<unsigned>() + (size_t)b0 * FL_BINS);
     }));
+    // Pipelined (device-resident input): the sweep goes to the low-priority side stream behind this D1 and may run beside
+    // D1 of the NEXT decode; the scratch both touch is this decode's own bank.  D1 keeps its full occupancy (measured:
+    // giving up a CTA per SM so that sweep CTAs fit beside it costs D1 20 % at B = 1024 - more than the overlap returns),
+    // so what overlaps is the launch latency, D1's ramp and tail and the sweep's: 2 % at B = 1024, 10 % at B = 128,
+    // 35 % at B = 32.
+    cudaStream_t ns = pipe ? d->stream_nms : st;
+    if (pipe) {
+        SSDC_CUDA(cudaEventRecord(d->ev_d1[d->bank], st));
+        SSDC_CUDA(cudaStreamWaitEvent(ns, d->ev_d1[d->bank], 0));
+    }
     SSDC_TRY(d->pad_rows.ensure((size_t)B * g.K * 6 * sizeof(double)));
     SSDC_TRY(d->pad_anchor.ensure((size_t)B * g.K * sizeof(int)));
     {
@@ -2069,16 +2079,20 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed&
         const size_t dyn = (size_t)g.C * ((narrow ? 128 : 256) / 32 + SW_KW) * sizeof(unsigned);
         if (narrow) {
             SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, st>>>(
+            sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, ns>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
                 g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         } else {
             SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, dyn, st>>>(
+            sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, dyn, ns>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
                 g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         }
         SSDC_TRY(check_launch("sweep_kernel"));
+    }
+    if (pipe) {
+        SSDC_CUDA(cudaEventRecord(d->ev_sweep[d->bank], ns));
+        d->sweep_pending[d->bank] = true;
     }
     if (g.have_hist) d->hist_clean = true;
     // (the packed row offsets are only needed for the host copy: scan_counts_kernel runs at collect time)
@@ -2087,7 +2101,7 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed&
 
 template <typename InT, typename IouT, bool TF>
 static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed& feed, const DecodeArgs& g, int64_t B,
-                        double conf_thresh, int cmp_f32_rn) {
+                        double conf_thresh, int cmp_f32_rn, bool pipe) {
     typedef typename KeyOf<InT>::type KeyT;
     const bool fast = (g.NS == 1);
     const size_t nseg = (size_t)g.nseg;
@@ -2115,7 +2129,7 @@ static int run_pipeline(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFe
     }
 
     SSDC_CUDA(cudaMemsetAsync(ints, 0, (L.kept_count) * sizeof(int), st));
-    if (g.sweep) return run_sweep<InT, IouT, TF>(ctx, d, y_dev, feed, g, B, thr);
+    if (g.sweep) return run_sweep<InT, IouT, TF>(ctx, d, y_dev, feed, g, B, thr, pipe);
     const int n1 = SORT_BYTES1 / (int)sizeof(KeyT), n2 = SORT_BYTES2 / (int)sizeof(KeyT), n3 = SORT_BYTES3 / (int)sizeof(KeyT);
 
     // D1
@@ -2298,6 +2312,12 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
         feed.src = reinterpret_cast<const char*>(y_pred);           // copied chunk by chunk, D1 behind every chunk (feed_chunks)
         feed.img_bytes = (size_t)A * g.W * elem;
     }
+    // consecutive device-resident image-sweep decodes are pipelined: this one takes the other scratch bank and only waits
+    // for the sweep that used it two decodes ago; everything else waits for every sweep still in flight (it shares the
+    // current bank, or overwrites the staged input the sweep decodes its boxes from)
+    const bool pipe = g.sweep && on_device && !ctx->profile && ctx->opt[SSDC_OPT_NO_PIPELINE] == 0;
+    if (pipe) { d->swap_banks(); SSDC_TRY(d->wait_sweeps(d->bank)); }
+    else SSDC_TRY(d->wait_sweeps());
     const size_t nseg = (size_t)g.nseg;
     IntLayout L = int_layout(nseg);
     SSDC_TRY(d->ints.ensure(L.total_ints * sizeof(int)));
@@ -2309,11 +2329,11 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
 
     int r;
     if (dtype == SSDC_F32) {
-        if (!iou_f32) r = run_pipeline<float, double, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
-        else if (!tf) r = run_pipeline<float, float, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
-        else r = run_pipeline<float, float, true>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
+        if (!iou_f32) r = run_pipeline<float, double, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn, pipe);
+        else if (!tf) r = run_pipeline<float, float, false>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn, pipe);
+        else r = run_pipeline<float, float, true>(ctx, d, (const float*)y_dev, feed, g, B, p->conf_thresh, cmp_rn, pipe);
     } else {
-        r = run_pipeline<double, double, false>(ctx, d, (const double*)y_dev, feed, g, B, p->conf_thresh, cmp_rn);
+        r = run_pipeline<double, double, false>(ctx, d, (const double*)y_dev, feed, g, B, p->conf_thresh, cmp_rn, pipe);
     }
     SSDC_TRY(r);
 
@@ -2342,6 +2362,7 @@ int decode_finish_dev(ssdc_ctx* ctx, DevCtx* d, int64_t* total_rows) {
     if (!job.valid) { set_error("ssdc_decode_collect without a submitted decode"); return SSDC_ERR_STATE; }
     if (job.B == 0) return SSDC_OK;
     SSDC_CUDA(cudaSetDevice(d->device));
+    SSDC_TRY(d->wait_sweeps());
     if (job.scan_pending) {
         LaunchScope ls(ctx, d, SSDC_K_MERGE);
         scan_counts_kernel<<<1, 1024, 0, d->stream>>>(d->out_count.as<int>(), (int)job.B, d->row_offset.as<long long>());
@@ -2399,6 +2420,7 @@ int greedy_nms_dev(ssdc_ctx* ctx, DevCtx* d, const double* boxes, const double* 
     *n_keep = 0;
     if (n == 0) return SSDC_OK;
     d->job.valid = false;            // shares the decode scratch: a pending decode is invalidated
+    SSDC_TRY(d->wait_sweeps());
     cudaStream_t st = d->stream;
     DecodeArgs g;
     memset(&g, 0, sizeof(g));

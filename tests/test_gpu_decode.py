@@ -440,3 +440,62 @@ def test_host_input_paths_agree(mode, ctx):
                     assert np.array_equal(a, b), (chunk_mb, src is y)
     finally:
         ctx.set_option('h2d_chunk_mb', 0)
+
+
+def test_pipelined_device_decodes(ctx):
+    """Consecutive device-resident decodes are pipelined (the NMS sweep of one runs on a side stream beside the filter
+    pass of the next, each decode in its own scratch bank): whatever is submitted in between, the collected decode
+    must equal the unpipelined result of ITS input, and the per-image rows left on the device by the last decode too."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    anchors = synth.anchors_of(enc)
+    B = 24
+    ys = [synth.synth_y_pred(anchors, enc.variances, 21, B, 90 + i, bg_bias=[8.0, 6.0, 7.0][i], hot=40) for i in range(3)]
+    args = (_lib.MODE_PER_CLASS, 0.01, 0.45, 200, 'centroids', True, 300, 300, 'half')
+    ctx.set_option('no_pipeline', 1)
+    try:
+        want = [_lib.run_decode(y, *args, ctx=ctx) for y in ys]
+    finally:
+        ctx.set_option('no_pipeline', 0)
+    p = _lib.DecodeParams()
+    p.mode, p.input_coords, p.normalize, p.border_pixels = _lib.MODE_PER_CLASS, 0, 1, 0
+    p.top_k, p.nms_cap, p.log_wh, p.do_nms = 200, 0, 1, 1
+    p.conf_thresh, p.iou_thresh, p.img_h, p.img_w = 0.01, 0.45, 300.0, 300.0
+    d = [ctx.dev_alloc(y.nbytes) for y in ys]
+    for dd, y in zip(d, ys):
+        ctx.h2d(dd, y)
+    lib = ctx.lib
+
+    def submit(i):
+        _lib.check(lib.ssdc_decode_submit(ctx.handle, d[i], _lib.F32, 1, B, 8732, 21, _lib.C.byref(p)))
+
+    def collect():
+        counts = np.zeros(B, np.int32)
+        total = _lib.C.c_int64(0)
+        rows = np.empty((B * 200, 6))
+        idx = np.empty(B * 200, np.int32)
+        _lib.check(lib.ssdc_decode_collect(ctx.handle, _lib.ptr(rows), B * 200, _lib.ptr(counts), _lib.ptr(idx), _lib.C.byref(total)))
+        n = int(total.value)
+        return rows[:n], counts, idx[:n]
+    try:
+        for order in ([0, 1, 2], [2, 2, 0, 1], [1], [0, 1, 0, 1, 0, 2, 1]):
+            for i in order:
+                submit(i)
+            got = collect()
+            for a, b in zip(got, want[order[-1]]):
+                assert np.array_equal(a, b), order
+        # interleaved with a host-input decode and a general-path decode (they share / wait for the banks)
+        submit(0); submit(1)
+        host = _lib.run_decode(ys[2], *args, ctx=ctx)
+        for a, b in zip(host, want[2]):
+            assert np.array_equal(a, b)
+        submit(1); submit(0)
+        fast = _lib.run_decode(ys[2], _lib.MODE_FAST, 0.3, 0.45, 'all', 'centroids', True, 300, 300, 'half', ctx=ctx)
+        submit(2)
+        got = collect()
+        for a, b in zip(got, want[2]):
+            assert np.array_equal(a, b)
+        assert fast[1].sum() > 0
+    finally:
+        ctx.synchronize()
+        for dd in d:
+            ctx.dev_free(dd)
