@@ -295,6 +295,37 @@ int ssdc_voc_match(ssdc_ctx* ctx, const int32_t* pred_image, const float* pred_c
                    int64_t n_images, double iou_threshold, int border_pixels, int only_first,
                    int32_t* out_order, int32_t* out_tp, int32_t* out_fp, int32_t* out_ctp, int32_t* out_cfp);
 
+/* ---- decoder -> evaluator glue, augmentation box checks -----------
+ * apply_inverse_transforms   data_generator/object_detection_2d_misc_utils.py:22-73 for the inverters the
+ * reference's own transformations return: Resize (object_detection_2d_geometric_ops.py:75-79: scale by
+ * original / resized size, np.round to 0 decimals), the patch samplers (object_detection_2d_patch_sampling_ops.py
+ * :316-320 translate; :577, :730 identity).  `rows` (n, width) float64 host array, modified in place; image i owns
+ * rows [row_offsets[i], row_offsets[i+1]) and the inverter steps [step_offsets[i], step_offsets[i+1]) of `steps`,
+ * three doubles each: kind (0 identity, 1 scale + round, 2 translate), value for the y columns, value for the x
+ * columns; applied in order. */
+int ssdc_inverse_transform_rows(ssdc_ctx* ctx, double* rows, int64_t n, int width, const int64_t* row_offsets, int64_t B,
+                                const double* steps, const int64_t* step_offsets,
+                                int xmin_col, int ymin_col, int xmax_col, int ymax_col);
+
+/* The per-class result lists of Evaluator.predict_on_dataset (eval_utils/average_precision_evaluator.py:402-422)
+ * straight from the device-resident rows of the last image-sweep decode (see ssdc_decode_results_dev): inverse
+ * transforms as above (`steps` may be NULL), confidence rounded to `round_conf_decimals` decimals (< 0: not
+ * rounded, the reference's default), coordinates rounded to one decimal, fields narrowed to float32 like the
+ * reference's structured array (:668-675).  Records come in (image, row) order: out_image = index of the image in the
+ * decoded batch, out_class, out_conf, out_box (xmin, ymin, xmax, ymax).  SSDC_ERR_CAPACITY if `capacity` records do not
+ * suffice (B * top_k always does). */
+int ssdc_results_for_evaluation(ssdc_ctx* ctx, const double* steps, const int64_t* step_offsets, int round_conf_decimals,
+                                int32_t* out_image, int32_t* out_class, float* out_conf, float* out_box,
+                                int64_t capacity, int64_t* n_out);
+
+/* BoxFilter.__call__   data_generator/object_detection_2d_image_boxes_validation_utils.py:174-232 for the boxes of
+ * one or many images: `boxes` (n, 4) xmin, ymin, xmax, ymax, `image_hw` (n, 2) height and width of the image each box
+ * is checked against; criterion 0 'center_point', 1 'iou', 2 'area'.  out_keep[i] = 1 if box i meets every enabled
+ * requirement. */
+int ssdc_box_filter(ssdc_ctx* ctx, const double* boxes, const double* image_hw, int64_t n,
+                    int check_degenerate, int check_min_area, int check_overlap, int criterion,
+                    double lower, double upper, double min_area, int border_pixels, uint8_t* out_keep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,9 @@ SIGNATURES = {
     'ssdc_match_bipartite_greedy': (_i, [_vp, _vp, _i64, _i64, _vp]),
     'ssdc_match_multi': (_i, [_vp, _vp, _i64, _i64, _d, _vp, _vp, _pi64]),
     'ssdc_ssd_loss': (_i, [_vp, _vp, _i, _vp, _i, _i64, _i64, _i, _i, _i, _d, _vp]),
+    'ssdc_inverse_transform_rows': (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i, _i]),
+    'ssdc_results_for_evaluation': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _pi64]),
+    'ssdc_box_filter': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _d, _d, _d, _i, _vp]),
     'ssdc_voc_match': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -27,7 +27,7 @@ LIBPATH = os.path.join(LIBDIR, 'libssdcodec.so')
 STAMP = os.path.join(LIBDIR, 'libssdcodec.stamp')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-SOURCES = ['ctx.cu', 'decode.cu', 'encode.cu', 'thin.cu', 'voc.cu', 'loss.cu']
+SOURCES = ['ctx.cu', 'decode.cu', 'encode.cu', 'thin.cu', 'voc.cu', 'loss.cu', 'evalprep.cu']
 NVCC_FLAGS = [
     '-O3', '-std=c++17',
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -143,6 +143,13 @@ struct DevCtx {
             if (e != cudaSuccess) { set_error("cudaEventSynchronize(staging) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
             h_busy[s] = false;
         }
+        if (!h_ring[s].p) {
+            // first use: every slot of the ring is allocated now (a page-locked allocation costs milliseconds; it must not
+            // land in the fourth call of a steady loop)
+            const size_t want = bytes > ((size_t)256 << 10) ? bytes + (bytes >> 2) : ((size_t)256 << 10);
+            for (int k = 0; k < H_RING; ++k)
+                if (!h_ring[k].p) { int r = h_ring[k].ensure(want); if (r != SSDC_OK) return r; }
+        }
         int r = h_ring[s].ensure(bytes);
         if (r != SSDC_OK) return r;
         *out = h_ring[s].p; *slot_out = s;

@@ -42,6 +42,7 @@ class DeviceEvaluator(object):
         self.gt_format = gt_format
         self.ignore_under_area = ignore_under_area
         self.prediction_results = None
+        self._acc = None                 # flat records of add_decoded_batch (alternative to prediction_results)
         self.num_gt_per_class = None
         self.true_positives = None
         self.false_positives = None
@@ -56,6 +57,68 @@ class DeviceEvaluator(object):
     def set_predictions(self, prediction_results):
         """`prediction_results[class_id]` = list of `(image_id, confidence, xmin, ymin, xmax, ymax)`."""
         self.prediction_results = prediction_results
+        self._acc = None
+
+    def reset_predictions(self):
+        self.prediction_results = None
+        self._acc = None
+
+    def add_decoded_batch(self, batch_image_ids, inverse_transforms=None, round_confidences=False):
+        """The body of the reference's prediction loop after `model.predict` (:381-422) without a Python loop over the
+        detections: takes the result of the LAST `decode_detections` call of this process (or `ssdc_decode_submit`
+        on a device-resident batch) where it lies - in device memory -, maps the boxes back to the original images
+        (`inverse_transforms`: per image a list of the inverters the reference's Resize / patch samplers return, or
+        the descriptor objects of data_generator.object_detection_2d_misc_utils), rounds confidences / coordinates
+        like :411-418 and appends flat records that `match_predictions` hands to the device matcher as they are.
+        Needs the image-sweep decode (finite `top_k`, float32 predictions)."""
+        try:
+            from ..data_generator import object_detection_2d_misc_utils as mu
+        except ImportError:
+            from data_generator import object_detection_2d_misc_utils as mu
+        n_img = len(batch_image_ids)
+        steps = step_offs = None
+        if inverse_transforms is not None:
+            plan = mu.compile_inverse_transforms(inverse_transforms, n_img)
+            if plan is None or tuple(plan[2]) != (self.pred_format['xmin'], self.pred_format['ymin'], self.pred_format['xmax'], self.pred_format['ymax']):
+                raise ValueError("add_decoded_batch only takes the affine inverters of the reference's transformations; for arbitrary "
+                                 "callables use decode_detections + apply_inverse_transforms + set_predictions.")
+            steps, step_offs = plan[0], plan[1]
+        ctx = _lib.get_context()
+        cap = 1 << 12
+        while True:
+            img = np.empty(cap, np.int32); cls = np.empty(cap, np.int32)
+            conf = np.empty(cap, np.float32); box = np.empty((cap, 4), np.float32)
+            n = _lib.C.c_int64(0)
+            rc = ctx.lib.ssdc_results_for_evaluation(ctx.handle, _lib.ptr(steps), _lib.ptr(step_offs),
+                                                     int(round_confidences) if round_confidences else -1,
+                                                     _lib.ptr(img), _lib.ptr(cls), _lib.ptr(conf), _lib.ptr(box), cap, _lib.C.byref(n))
+            if rc == _lib.ERR_CAPACITY and cap < (1 << 28):
+                cap *= 8
+                continue
+            _lib.check(rc)
+            break
+        n = int(n.value)
+        if n and int(img[:n].max()) >= n_img:
+            raise ValueError("the decoded batch holds more images than `batch_image_ids`")
+        ids = np.asarray([str(x) for x in batch_image_ids], dtype=object)
+        if getattr(self, '_acc', None) is None:
+            self._acc = {'ids': [], 'cls': [], 'conf': [], 'box': []}
+        self._acc['ids'].append(ids[img[:n]])
+        self._acc['cls'].append(cls[:n].copy())
+        self._acc['conf'].append(conf[:n].copy())
+        self._acc['box'].append(box[:n].copy())
+        return n
+
+    def materialize_prediction_results(self):
+        """`prediction_results` in the reference's list-of-tuples structure (:405-422) from the records collected by
+        `add_decoded_batch` (for `write_predictions_to_txt` and other consumers of the original structure)."""
+        if getattr(self, '_acc', None) is None:
+            return self.prediction_results
+        res = [list() for _ in range(self.n_classes + 1)]
+        for ids, cls, conf, box in zip(self._acc['ids'], self._acc['cls'], self._acc['conf'], self._acc['box']):
+            for i in range(len(cls)):
+                res[int(cls[i])].append((ids[i], float(conf[i]), float(box[i, 0]), float(box[i, 1]), float(box[i, 2]), float(box[i, 3])))
+        return res
 
     def predict_on_dataset(self, *args, **kwargs):
         raise NotImplementedError("predict_on_dataset needs the Keras model and the data generator, which are outside "
@@ -66,8 +129,8 @@ class DeviceEvaluator(object):
                  border_pixels='include', sorting_algorithm='quicksort', return_precisions=False,
                  return_recalls=False, return_average_precisions=False, verbose=True, **unused):
         """The evaluation part of the reference's `__call__` (:97-259), starting from `prediction_results`."""
-        if self.prediction_results is None:
-            raise ValueError("There are no prediction results. Provide them with `set_predictions()`.")
+        if self.prediction_results is None and getattr(self, '_acc', None) is None:
+            raise ValueError("There are no prediction results. Provide them with `set_predictions()` or `add_decoded_batch()`.")
         self.get_num_gt_per_class(ignore_neutral_boxes=ignore_neutral_boxes, verbose=False, ret=False)
         self.match_predictions(ignore_neutral_boxes=ignore_neutral_boxes, matching_iou_threshold=matching_iou_threshold,
                                border_pixels=border_pixels, sorting_algorithm=sorting_algorithm, verbose=verbose, ret=False)
@@ -134,7 +197,7 @@ class DeviceEvaluator(object):
         reference's behaviour of evaluating only the best prediction of every class (:692-696)."""
         if self.data_generator.labels is None:
             raise ValueError("Matching predictions to ground truth boxes not possible, no ground truth given.")
-        if self.prediction_results is None:
+        if self.prediction_results is None and getattr(self, '_acc', None) is None:
             raise ValueError("There are no prediction results. You must run `predict_on_dataset()` before calling this method.")
         if border_pixels not in _lib.BORDER:
             raise ValueError("`border_pixels` must be one of 'half', 'include' and 'exclude'.")
@@ -162,19 +225,32 @@ class DeviceEvaluator(object):
         # predictions, flattened per class ('f4' fields like the reference's structured array, :668-675)
         C = self.n_classes
         coff = np.zeros(C + 2, dtype=np.int64)
-        imgs, confs, boxes = [], [], []
-        for c in range(1, C + 1):
-            preds = self.prediction_results[c]
-            coff[c + 1] = coff[c] + len(preds)
-            if len(preds):
-                imgs.append(np.fromiter((index_of[str(p[0])] for p in preds), dtype=np.int32, count=len(preds)))
-                arr = np.array([p[1:6] for p in preds], dtype=np.float64).astype(np.float32)
-                confs.append(arr[:, 0])
-                boxes.append(arr[:, 1:5])
+        if getattr(self, '_acc', None) is not None and self.prediction_results is None:
+            # flat records of add_decoded_batch: a stable sort by class gives the per-class lists in append order
+            cls_all = np.concatenate(self._acc['cls']) if self._acc['cls'] else np.zeros(0, np.int32)
+            ids_all = np.concatenate(self._acc['ids']) if self._acc['ids'] else np.zeros(0, object)
+            by_class = np.argsort(cls_all, kind='stable')
+            by_class = by_class[(cls_all[by_class] >= 1) & (cls_all[by_class] <= C)]
+            coff[2:] = np.cumsum(np.bincount(cls_all[by_class], minlength=C + 1)[1:C + 1])
+            uniq, inv = np.unique(ids_all, return_inverse=True) if len(ids_all) else (np.zeros(0, object), np.zeros(0, np.int64))
+            lut = np.array([index_of[u] for u in uniq], dtype=np.int32) if len(uniq) else np.zeros(0, np.int32)
+            pim = np.ascontiguousarray(lut[inv][by_class]) if len(ids_all) else np.zeros(0, np.int32)
+            pcf = np.ascontiguousarray(np.concatenate(self._acc['conf'])[by_class]) if len(ids_all) else np.zeros(0, np.float32)
+            pbx = np.ascontiguousarray(np.concatenate(self._acc['box'], axis=0)[by_class]) if len(ids_all) else np.zeros((0, 4), np.float32)
+        else:
+            imgs, confs, boxes = [], [], []
+            for c in range(1, C + 1):
+                preds = self.prediction_results[c]
+                coff[c + 1] = coff[c] + len(preds)
+                if len(preds):
+                    imgs.append(np.fromiter((index_of[str(p[0])] for p in preds), dtype=np.int32, count=len(preds)))
+                    arr = np.array([p[1:6] for p in preds], dtype=np.float64).astype(np.float32)
+                    confs.append(arr[:, 0])
+                    boxes.append(arr[:, 1:5])
+            pim = np.ascontiguousarray(np.concatenate(imgs)) if imgs else np.zeros(0, np.int32)
+            pcf = np.ascontiguousarray(np.concatenate(confs)) if confs else np.zeros(0, np.float32)
+            pbx = np.ascontiguousarray(np.concatenate(boxes, axis=0)) if boxes else np.zeros((0, 4), np.float32)
         P = int(coff[C + 1])
-        pim = np.ascontiguousarray(np.concatenate(imgs)) if imgs else np.zeros(0, np.int32)
-        pcf = np.ascontiguousarray(np.concatenate(confs)) if confs else np.zeros(0, np.float32)
-        pbx = np.ascontiguousarray(np.concatenate(boxes, axis=0)) if boxes else np.zeros((0, 4), np.float32)
         order = np.empty(max(P, 1), np.int32)
         tp = np.empty(max(P, 1), np.int32)
         fp = np.empty(max(P, 1), np.int32)

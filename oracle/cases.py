@@ -258,3 +258,58 @@ def build_voc_input(case):
                              round(float(box[2]), 1), round(float(box[3]), 1)))
     return dict(labels=labels, eval_neutral=neutral if case.get('neutral') else None, image_ids=image_ids,
                 prediction_results=preds, n_classes=C)
+
+
+# ----------------------------------------------------------------------------------------
+# decoder -> evaluator glue and BoxFilter: seeded inputs
+# ----------------------------------------------------------------------------------------
+def build_evalprep_input(seed=11, n_images=9):
+    """Decoded predictions of a batch (float64 (k_i, 6), one image empty), per-image inverter specifications
+    ('resize', H, W, out_h, out_w) / ('translate', dy, dx) / ('identity',) / None, and label arrays for BoxFilter."""
+    rng = np.random.default_rng(seed)
+    preds, specs = [], []
+    for i in range(n_images):
+        k = 0 if i == 3 else int(rng.integers(1, 40))
+        p = np.zeros((k, 6))
+        p[:, 0] = rng.integers(1, 21, size=k)
+        p[:, 1] = rng.uniform(0.01, 1.0, size=k)
+        x0 = rng.uniform(-20, 280, size=k); y0 = rng.uniform(-20, 280, size=k)
+        p[:, 2], p[:, 3] = x0, y0
+        p[:, 4], p[:, 5] = x0 + rng.uniform(1, 150, size=k), y0 + rng.uniform(1, 150, size=k)
+        # values that sit on rounding boundaries (x.5 after scaling, x.x5 for the one-decimal rounding)
+        if k > 2:
+            p[0, 2:6] = [10.25, 20.75, 30.05, 40.15]
+            p[1, 2:6] = [0.5, 1.5, 2.5, 3.5]
+        preds.append(p)
+        H, W = int(rng.integers(200, 700)), int(rng.integers(200, 700))
+        kind = i % 4
+        if kind == 0:
+            specs.append([('resize', H, W, 300, 300)])
+        elif kind == 1:
+            specs.append([('translate', int(rng.integers(-50, 50)), int(rng.integers(-50, 50))), ('resize', H, W, 300, 300)])
+        elif kind == 2:
+            specs.append([('identity',), None, ('resize', 2 * H, W, 300, 300), ('translate', 7, -3)])
+        else:
+            specs.append([])
+    labels = []
+    for i in range(12):
+        m = 0 if i == 5 else int(rng.integers(1, 25))
+        l = np.zeros((m, 5))
+        l[:, 0] = rng.integers(1, 21, size=m)
+        x0 = np.floor(rng.uniform(-60, 320, size=m)); y0 = np.floor(rng.uniform(-60, 320, size=m))
+        l[:, 1], l[:, 2] = x0, y0
+        l[:, 3] = x0 + np.floor(rng.uniform(-2, 120, size=m))        # some degenerate, some tiny
+        l[:, 4] = y0 + np.floor(rng.uniform(-2, 120, size=m))
+        labels.append(l)
+    return dict(preds=preds, specs=specs, labels=labels)
+
+
+BOXFILTER_CONFIGS = [
+    dict(),
+    dict(overlap_criterion='iou', overlap_bounds=(0.1, 0.9)),
+    dict(overlap_criterion='area', overlap_bounds=(0.3, 1.0)),
+    dict(overlap_criterion='area', overlap_bounds=(0.0, 1.0), border_pixels='include'),
+    dict(overlap_criterion='iou', overlap_bounds=(0.0, 0.5), border_pixels='exclude', check_min_area=False),
+    dict(check_overlap=False, min_area=400),
+    dict(overlap_criterion='center_point', check_degenerate=False, check_min_area=False),
+]

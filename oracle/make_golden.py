@@ -201,6 +201,67 @@ def golden_voc(evmod, case):
                                                       sum(int(np.sum(tp[c])) for c in range(1, C + 1)), float(np.mean(ap_s[1:]))))
 
 
+def golden_evalprep():
+    """Decoder -> evaluator glue and BoxFilter: the reference's own functions and inverter closures on the seeded
+    inputs; the numpy restatement must agree bit for bit."""
+    from oracle import eval_prep_oracle as ep
+    ns = ref_loader.load_data_generator_utils()
+    inp = cases.build_evalprep_input()
+    ref_inv = [ref_loader.reference_inverters(ns, sp) for sp in inp['specs']]
+    r = ns.misc.apply_inverse_transforms([np.copy(p) for p in inp['preds']], ref_inv)
+
+    def orc_inverters(specs):
+        out = []
+        for sp in specs:
+            if sp is None:
+                out.append(None)
+            elif sp[0] == 'resize':
+                out.append(ep.resize_inverter(*sp[1:]))
+            elif sp[0] == 'translate':
+                out.append(ep.translate_inverter(*sp[1:]))
+            else:
+                out.append(lambda labels: labels)
+        return out
+    o = ep.apply_inverse_transforms(inp['preds'], [orc_inverters(sp) for sp in inp['specs']])
+    assert all(same(a, b) for a, b in zip(r, o))
+    out = {}
+    for i, a in enumerate(r):
+        out['inv_%d' % i] = np.asarray(a)
+    # result records: the loop of average_precision_evaluator.py:405-422, executed literally on the reference's output
+    for rc in (False, 2):
+        img, cls, conf, box = [], [], [], []
+        for k, batch_item in enumerate(r):
+            for b in np.asarray(batch_item).reshape(-1, 6):
+                img.append(k); cls.append(int(b[0]))
+                conf.append(round(b[1], rc) if rc else b[1])
+                box.append([round(b[2], 1), round(b[3], 1), round(b[4], 1), round(b[5], 1)])
+        rec = np.array([tuple([c] + bx) for c, bx in zip(conf, box)], dtype=[('c', 'f4'), ('x0', 'f4'), ('y0', 'f4'), ('x1', 'f4'), ('y1', 'f4')])
+        oi, oc, of, ob = ep.evaluation_records(o, rc)
+        assert same(np.array(img, np.int32), oi) and same(np.array(cls, np.int32), oc) and same(rec['c'], of)
+        assert same(np.stack([rec['x0'], rec['y0'], rec['x1'], rec['y1']], 1), ob)
+        tag = 'rc%d' % int(rc)
+        out['rec_img_' + tag], out['rec_cls_' + tag], out['rec_conf_' + tag], out['rec_box_' + tag] = oi, oc, of, ob
+    # BoxFilter
+    for ci, cfg in enumerate(cases.BOXFILTER_CONFIGS):
+        bf = ns.validation.BoxFilter(**cfg)
+        for li, lab in enumerate(inp['labels']):
+            H, W = 300 + 7 * li, 280 + 11 * li
+            want = bf(lab, image_height=H, image_width=W)
+            lower, upper = cfg.get('overlap_bounds', (0.3, 1.0))
+            mask = ep.box_filter(lab, H, W, check_overlap=cfg.get('check_overlap', True), check_min_area=cfg.get('check_min_area', True),
+                                 check_degenerate=cfg.get('check_degenerate', True), overlap_criterion=cfg.get('overlap_criterion', 'center_point'),
+                                 lower=lower, upper=upper, min_area=cfg.get('min_area', 16), border_pixels=cfg.get('border_pixels', 'half'))
+            assert same(np.asarray(want), lab[mask]), (ci, li)
+            out['bf_%d_%d' % (ci, li)] = mask
+    # ImageValidator on the same labels
+    iv = ns.validation.ImageValidator(overlap_criterion='area', bounds=(0.5, 1.0), n_boxes_min=3)
+    out['iv_area3'] = np.array([bool(iv(lab, 300, 300)) if len(lab) else False for lab in inp['labels']])
+    iv = ns.validation.ImageValidator(overlap_criterion='center_point', n_boxes_min='all')
+    out['iv_all'] = np.array([bool(iv(lab, 300, 300)) for lab in inp['labels']])
+    np.savez_compressed(os.path.join(GOLDEN, 'evalprep.npz'), **out)
+    print('evalprep: %d arrays' % len(out))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_loader.load()
@@ -214,6 +275,8 @@ def main():
             golden_encode(ref, case)
     if not only or 'thin' in only:
         golden_thin(ref)
+    if not only or 'evalprep' in only:
+        golden_evalprep()
     evmod = ref_loader.load_evaluator()
     for case in cases.VOC_CASES:
         if not only or case['name'] in only:

@@ -88,3 +88,65 @@ def load_evaluator():
         for name in added:
             sys.modules.pop(name, None)
     return mod
+
+
+def load_data_generator_utils():
+    """The reference's geometric / patch-sampling operations, box validation utilities and misc utils.  `cv2` is absent
+    here and only touches pixels: a stub with the interpolation constants and a `resize` that returns an array of the
+    requested size is enough for the label arithmetic and the inverters.  `np.bool` (removed from numpy) is re-created
+    as the builtin it aliased (image_boxes_validation_utils.py:183)."""
+    import types
+    if not available():
+        raise RuntimeError('reference not present at ' + REF_ROOT)
+    for name, val in (('float', float), ('int', int), ('bool', bool)):
+        if not hasattr(np, name):
+            setattr(np, name, val)
+    cv2 = types.ModuleType('cv2')
+    for i, name in enumerate(['INTER_NEAREST', 'INTER_LINEAR', 'INTER_CUBIC', 'INTER_AREA', 'INTER_LANCZOS4']):
+        setattr(cv2, name, i)
+    cv2.resize = lambda image, dsize, interpolation=1: np.zeros((dsize[1], dsize[0]) + tuple(image.shape[2:]), dtype=image.dtype)
+    had_cv2 = sys.modules.get('cv2')
+    sys.modules['cv2'] = cv2
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k.split('.')[0] in ('ssd_encoder_decoder', 'bounding_box_utils', 'data_generator')}
+    sys.path.insert(0, REF_ROOT)
+    try:
+        class NS(object):
+            pass
+        ns = NS()
+        ns.misc = importlib.import_module('data_generator.object_detection_2d_misc_utils')
+        ns.validation = importlib.import_module('data_generator.object_detection_2d_image_boxes_validation_utils')
+        ns.geometric = importlib.import_module('data_generator.object_detection_2d_geometric_ops')
+        ns.patch = importlib.import_module('data_generator.object_detection_2d_patch_sampling_ops')
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k in list(sys.modules):
+            if k.split('.')[0] in ('ssd_encoder_decoder', 'bounding_box_utils', 'data_generator'):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+        if had_cv2 is None:
+            sys.modules.pop('cv2', None)
+        else:
+            sys.modules['cv2'] = had_cv2
+    return ns
+
+
+def reference_inverters(ns, specs):
+    """Inverter closures of the REAL transformation classes for a list of specifications (oracle/cases.py)."""
+    out = []
+    for spec in specs:
+        if spec is None:
+            out.append(None)
+        elif spec[0] == 'resize':
+            _, H, W, oh, ow = spec
+            _, inv = ns.geometric.Resize(height=oh, width=ow)(np.zeros((H, W, 3), np.uint8), return_inverter=True)
+            out.append(inv)
+        elif spec[0] == 'translate':
+            _, dy, dx = spec
+            # (CropPad copies `labels` before testing it for None, so it must be given some)
+            res = ns.patch.CropPad(patch_ymin=dy, patch_xmin=dx, patch_height=400, patch_width=400)(
+                np.zeros((300, 300, 3), np.uint8), np.zeros((1, 5)), return_inverter=True)
+            out.append(res[-1])
+        else:
+            out.append(lambda labels: labels)
+    return out

@@ -151,7 +151,9 @@ def test_drop_in_keeps_unreplaced_reference_modules(tmp_path):
     import sys
     fake = tmp_path / 'localisation_part'
     for pkg, mod in (('keras_layers', 'keras_layer_AnchorBoxes'), ('eval_utils', 'coco_utils'),
-                     ('eval_utils', 'average_precision_evaluator'), ('keras_layers', 'keras_layer_DecodeDetections')):
+                     ('eval_utils', 'average_precision_evaluator'), ('keras_layers', 'keras_layer_DecodeDetections'),
+                     ('data_generator', 'object_detection_2d_geometric_ops'), ('data_generator', 'object_detection_2d_misc_utils'),
+                     ('data_generator', 'object_detection_2d_image_boxes_validation_utils')):
         (fake / pkg).mkdir(parents=True, exist_ok=True)
         (fake / pkg / '__init__.py').write_text('')
         (fake / pkg / (mod + '.py')).write_text("ORIGIN = 'reference'\n")
@@ -161,7 +163,11 @@ def test_drop_in_keeps_unreplaced_reference_modules(tmp_path):
         "from eval_utils.average_precision_evaluator import Evaluator\n"
         "from keras_layers.keras_layer_DecodeDetections import DecodeDetections\n"
         "import eval_utils.average_precision_evaluator as m\n"
-        "assert a == b == 'reference' and not hasattr(m, 'ORIGIN')\n"
+        "from data_generator.object_detection_2d_geometric_ops import ORIGIN as c\n"
+        "from data_generator.object_detection_2d_misc_utils import apply_inverse_transforms\n"
+        "from data_generator.object_detection_2d_image_boxes_validation_utils import BoxFilter, ImageValidator, BoundGenerator\n"
+        "import data_generator.object_detection_2d_misc_utils as m2\n"
+        "assert a == b == c == 'reference' and not hasattr(m, 'ORIGIN') and not hasattr(m2, 'ORIGIN')\n"
         "print('ok')\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200'), str(fake)]))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', env=env)

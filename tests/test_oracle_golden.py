@@ -187,3 +187,75 @@ def test_tf_nms_restatement_reproduces_tensorflows_published_unit_test_answers()
         s = np.array(c['scores'], np.float32)
         got = orc._tf_nms(b, s, c['max_output_size'], c['iou_threshold'])
         assert got.tolist() == c['selected'], c['name']
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder -> evaluator glue and BoxFilter
+# ---------------------------------------------------------------------------------------------
+def _oracle_inverters(specs):
+    from oracle import eval_prep_oracle as ep
+    out = []
+    for sp in specs:
+        if sp is None:
+            out.append(None)
+        elif sp[0] == 'resize':
+            out.append(ep.resize_inverter(*sp[1:]))
+        elif sp[0] == 'translate':
+            out.append(ep.translate_inverter(*sp[1:]))
+        else:
+            out.append(lambda labels: labels)
+    return out
+
+
+def test_evalprep_oracle_matches_reference_goldens():
+    """apply_inverse_transforms with the Resize / patch-sampler inverters, the Evaluator's result records and
+    BoxFilter: the numpy restatement reproduces what the reference's own functions returned (tests/golden/evalprep.npz,
+    written by oracle/make_golden.py from the real classes)."""
+    from oracle import eval_prep_oracle as ep
+    g = load_golden('evalprep')
+    inp = cases.build_evalprep_input()
+    o = ep.apply_inverse_transforms(inp['preds'], [_oracle_inverters(sp) for sp in inp['specs']])
+    for i, a in enumerate(o):
+        assert np.array_equal(a, g['inv_%d' % i])
+    for rc in (False, 2):
+        tag = 'rc%d' % int(rc)
+        img, cls, conf, box = ep.evaluation_records(o, rc)
+        assert np.array_equal(img, g['rec_img_' + tag]) and np.array_equal(cls, g['rec_cls_' + tag])
+        assert np.array_equal(conf, g['rec_conf_' + tag]) and np.array_equal(box, g['rec_box_' + tag])
+    n_kept = 0
+    for ci, cfg in enumerate(cases.BOXFILTER_CONFIGS):
+        lower, upper = cfg.get('overlap_bounds', (0.3, 1.0))
+        for li, lab in enumerate(inp['labels']):
+            mask = ep.box_filter(lab, 300 + 7 * li, 280 + 11 * li, check_overlap=cfg.get('check_overlap', True),
+                                 check_min_area=cfg.get('check_min_area', True), check_degenerate=cfg.get('check_degenerate', True),
+                                 overlap_criterion=cfg.get('overlap_criterion', 'center_point'), lower=lower, upper=upper,
+                                 min_area=cfg.get('min_area', 16), border_pixels=cfg.get('border_pixels', 'half'))
+            assert np.array_equal(mask, g['bf_%d_%d' % (ci, li)]), (ci, li)
+            n_kept += int(mask.sum())
+    assert n_kept > 100
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference not present')
+def test_reference_inverter_closures_are_recognised():
+    """The drop-in recognises the closures the REAL Resize / CropPad return (by their free variables) and compiles them
+    into the same steps as the descriptor objects."""
+    from jpeg_detection_resnet_ssd_b200.data_generator import object_detection_2d_misc_utils as mu
+    ns = ref_loader.load_data_generator_utils()
+    inp = cases.build_evalprep_input()
+    for sp in inp['specs']:
+        real = ref_loader.reference_inverters(ns, sp)
+        plan = mu.compile_inverse_transforms([real], 1)
+        assert plan is not None
+        desc = []
+        for s in sp:
+            if s is None:
+                desc.append(None)
+            elif s[0] == 'resize':
+                desc.append(mu.ResizeInverter(*s[1:]))
+            elif s[0] == 'translate':
+                desc.append(mu.TranslateInverter(*s[1:]))
+            else:
+                desc.append(None)
+        plan2 = mu.compile_inverse_transforms([desc], 1)
+        assert np.array_equal(plan[0], plan2[0]) and np.array_equal(plan[1], plan2[1]) and tuple(plan[2]) == tuple(plan2[2])
+    assert mu.describe_inverter(lambda labels: labels * 2) is None          # arbitrary user code stays on the host path
