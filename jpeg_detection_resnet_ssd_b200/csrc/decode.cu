@@ -1078,13 +1078,67 @@ __device__ __forceinline__ void chunk_sort(unsigned long long* kA, unsigned long
     __syncthreads();
 }
 
+// Sorts kA[0..cn) descending IN PLACE (kB is scratch) by distributing the keys over the 1/16-octave score bins of the
+// histogram (a counting sort: the bins are monotone in the key order) and ranking every key inside its own bin.  A
+// slice of a few hundred candidates near the top of a score distribution spreads over dozens of bins with a handful of
+// keys each, so this is two shared-memory atomic passes, one warp scan and a short scan per key instead of a sorting
+// network.  Returns false (nothing changed) when a bin holds more than SW_BIN_MAX keys - score ties, saturated
+// confidences -; the caller then uses the sorting network.  `scratch`: 2 * FL_BINS words.
+constexpr int SW_BIN_MAX = 48;
+template <int SW_THREADS>
+__device__ __forceinline__ bool bin_sort(unsigned long long* kA, unsigned long long* kB, int cn, unsigned* scratch, int* s_flag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned* cnt = scratch;                 // keys per bin, then: first position of the bin
+    unsigned* fill = scratch + FL_BINS;      // next free position of the bin during the scatter
+    for (int i = tid; i < FL_BINS; i += SW_THREADS) cnt[i] = 0u;
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    for (int e = tid; e < cn; e += SW_THREADS) atomicAdd(&cnt[floor_bin_of_ord((unsigned)(kA[e] >> 32))], 1u);
+    __syncthreads();
+    if (warp == 0) {
+        unsigned c[8];
+        unsigned mine = 0, mx = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { c[q] = cnt[lane * 8 + q]; mine += c[q]; mx = c[q] > mx ? c[q] : mx; }
+        unsigned suffix = mine;              // keys in this lane's bins and above
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_down_sync(0xffffffffu, suffix, o);
+            if (lane + o < 32) suffix += v;
+        }
+        unsigned pos = suffix - mine;        // keys in higher bins: first position of this lane's top bin
+#pragma unroll
+        for (int q = 7; q >= 0; --q) { fill[lane * 8 + q] = pos; pos += c[q]; }
+        if (__any_sync(0xffffffffu, mx > (unsigned)SW_BIN_MAX) && lane == 0) *s_flag = 1;
+    }
+    __syncthreads();
+    if (*s_flag) return false;
+    // (cnt keeps the populations; the start of a bin is recovered as fill-after-scatter minus its population)
+    for (int e = tid; e < cn; e += SW_THREADS) {
+        const unsigned long long k = kA[e];
+        kB[atomicAdd(&fill[floor_bin_of_ord((unsigned)(k >> 32))], 1u)] = k;
+    }
+    __syncthreads();
+    for (int e = tid; e < cn; e += SW_THREADS) {
+        const unsigned long long k = kB[e];
+        const int bin = floor_bin_of_ord((unsigned)(k >> 32));
+        const int pop = (int)cnt[bin], s0 = (int)fill[bin] - pop;
+        int before = 0;
+        for (int j = 0; j < pop; ++j) before += kB[s0 + j] > k;
+        kA[s0 + before] = k;
+    }
+    __syncthreads();
+    return true;
+}
+
 template <typename IouT, bool TF, int SW_THREADS>
 __global__ void __launch_bounds__(SW_THREADS, SW_THREADS == 256 ? 3 : 7)
 sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_count, size_t img_stride,
              const float* __restrict__ y, DecodeArgs g, float conf_thr,
              int* __restrict__ g_floor, unsigned* __restrict__ g_hist, int* __restrict__ stats,
              double* __restrict__ pad_rows, int* __restrict__ pad_anchor, int* __restrict__ out_count) {
-    constexpr int SW_PANEL = SW_THREADS;                         // candidates resolved per NMS panel: thread <-> candidate
+    constexpr int SW_WARPS = SW_THREADS / 32;
+    constexpr int SW_PANEL = SW_THREADS;                         // candidates resolved per NMS panel
     constexpr int SW_PW = SW_PANEL / 32;
     extern __shared__ __align__(16) unsigned char sw_dyn[];      // cm[C][SW_PW] | km[C][SW_KW]
     __shared__ unsigned long long kA[SW_CHUNK];                  // slice as compacted (unsorted), sort scratch
@@ -1114,25 +1168,20 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
     const float thr_lo = (float)g.iou_thr * (1.0f - 2e-5f), thr_hi = (float)g.iou_thr * (1.0f + 2e-5f);
     const unsigned lt = (1u << lane) - 1u;
 
-    // the first reads of the kernel (count, floor, histogram, keys) do not depend on one another: the first 8 keys per
-    // thread are loaded now, speculatively (positions beyond the image's count hold stale keys and are masked when the
-    // count is known), so that the first compaction does not pay a second round trip
-    // (wide variant only: the narrow one runs at 7 CTAs per SM on a register budget that has no room for them and
-    // prefetches the lines to L2 instead)
-    constexpr bool PRELOAD = SW_THREADS == 256;
-    unsigned long long kpre[PRELOAD ? 8 : 1];
-    if (PRELOAD) {
-#pragma unroll
-        for (int u = 0; u < (PRELOAD ? 8 : 1); ++u) {
-            const size_t i = (size_t)u * SW_THREADS + tid;
-            kpre[u] = i < img_stride ? gk[i] : ~0ull;
-        }
-    } else {
-        const size_t lines = (img_stride * sizeof(unsigned long long) + 127) / 128;
-        for (size_t l = tid; l < lines && l < 2 * SW_CHUNK * sizeof(unsigned long long) / 128; l += SW_THREADS)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(gk) + l * 128));
+    // The first reads of the kernel (count, floor, histogram, keys) do not depend on one another: the head of the image's
+    // key list is copied into shared memory asynchronously (cp.async, no registers) while the count and the histogram are
+    // on their way, so that the first compaction does not pay a second round trip.  Positions beyond the image's count
+    // hold stale keys and are masked when the count is known.  The landing zone is `cbox`, which is idle until the slice's
+    // boxes are decoded.
+    constexpr int SW_PRE = SW_CHUNK * (int)sizeof(SBox<float>) / (int)sizeof(unsigned long long);      // 1024 keys
+    unsigned long long* kpre = reinterpret_cast<unsigned long long*>(cbox);
+    bool pre_valid = (img_stride & 1) == 0;                       // (16-byte alignment of every image's list)
+    const int n_pre = (int)(img_stride < (size_t)SW_PRE ? img_stride & ~(size_t)1 : (size_t)SW_PRE);
+    if (pre_valid) {
+        for (int i = 2 * tid; i < n_pre; i += 2 * SW_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(kpre + i)), "l"(gk + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    bool pre_valid = PRELOAD;
     int n = img_count[b];
     int F = 0;                                                    // floor bin: keys of the bins >= F are complete
     bool use_hist = g.have_hist != 0;
@@ -1318,18 +1367,14 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
             }
             // ------------------------------------------------------------ compact {tau <= key < hi} into shared memory
             if (tid == 0) s_cnt = 0;
+            if (pre_valid) asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
             for (int i0 = 0; i0 < n; i0 += 8 * SW_THREADS) {
                 unsigned long long k4[8];
-                if (PRELOAD && i0 == 0 && pre_valid) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) k4[u] = (u * SW_THREADS + tid < n) ? kpre[PRELOAD ? u : 0] : ~0ull;
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u * SW_THREADS + tid;
-                        k4[u] = (i < n) ? gk[i] : ~0ull;                     // (~0: never below `hi`)
-                    }
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * SW_THREADS + tid;
+                    k4[u] = (i < n) ? ((pre_valid && i < n_pre) ? kpre[i] : gk[i]) : ~0ull;      // (~0: never below `hi`)
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -1365,12 +1410,13 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                 break;
             }
             // ------------------------------------------------------------ sort, decode the boxes
-            chunk_sort<SW_THREADS>(kA, kB, cn);
+            unsigned long long* ks = kA;                   // the slice, sorted descending
+            if (!bin_sort<SW_THREADS>(kA, kB, cn, &sup[0][0], &s_done)) { chunk_sort<SW_THREADS>(kA, kB, cn); ks = kB; }
             for (int i = tid; i < cn; i += SW_THREADS) {
-                unsigned anc = ck_anchor(kB[i]);
-                if (anc >= (unsigned)g.A || ck_cls(kB[i]) >= C || ck_cls(kB[i]) < 1) {       // invariant: every staged key is a real candidate
-                    atomicCAS(&stats[CNT_STAT_ERR], 0, 1 + (ck_cls(kB[i]) >= C || ck_cls(kB[i]) < 1));
-                    anc = 0; kB[i] = (kB[i] & 0xffffffff00000000ull) | (0xfeull << 24) | 0xffffffull;
+                unsigned anc = ck_anchor(ks[i]);
+                if (anc >= (unsigned)g.A || ck_cls(ks[i]) >= C || ck_cls(ks[i]) < 1) {       // invariant: every staged key is a real candidate
+                    atomicCAS(&stats[CNT_STAT_ERR], 0, 1 + (ck_cls(ks[i]) >= C || ck_cls(ks[i]) < 1));
+                    anc = 0; ks[i] = (ks[i] & 0xffffffff00000000ull) | (0xfeull << 24) | 0xffffffull;
                 }
                 const SBox<float> bx = decode_box<float>(yb + (size_t)anc * g.W, g.C, g);
                 cbox[i] = bx;
@@ -1387,44 +1433,56 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                 for (int i = tid; i < C * SW_PW; i += SW_THREADS) cm[i] = 0u;
                 if (tid < SW_PW) dead[tid] = 0u;
                 __syncthreads();
-                for (int i = tid; i < P; i += SW_THREADS) atomicOr(&cm[(size_t)ck_cls(kB[p0 + i]) * SW_PW + (i >> 5)], 1u << (i & 31));
+                for (int i = tid; i < P; i += SW_THREADS) atomicOr(&cm[(size_t)ck_cls(ks[p0 + i]) * SW_PW + (i >> 5)], 1u << (i & 31));
                 __syncthreads();
-                for (int i = tid; i < P; i += SW_THREADS) {
-                    const int cls = ck_cls(kB[p0 + i]);
-                    const SBox<float> me = cbox[p0 + i];
-                    // (a) kept boxes of the same class
-                    bool is_dead = false;
+                // Work units of 32 lanes: (row r of the panel, word w <= r of the panel) = which earlier candidates of word w
+                // would suppress candidate 32 r + lane, and (row r, word of the kept list) = does a kept box suppress it.
+                // Row r has r + 1 + kwords units - dealt to the warps round robin, every warp gets the same share (with
+                // thread <-> candidate the last warp of the panel would do eight times the first one's work).
+                {
+                    const int R = (P + 31) >> 5;
                     const int kwords = (nkept + 31) >> 5;
-                    for (int w = 0; w < kwords && !is_dead; ++w) {
-                        for (unsigned rem = km[(size_t)cls * SW_KW + w]; rem; rem &= rem - 1) {
-                            const int k = (w << 5) + __ffs(rem) - 1;
-                            const SBox<float> kr = kraw[k];
-                            if (f32) {
-                                const int r = pair_f32(me, kr, thr_lo, thr_hi);
-                                if (r == 0) continue;
-                                if (r == 1) { is_dead = true; break; }
-                            } else if (screen && raw_disjoint(me, kr)) continue;
-                            if (decide_pair<float, IouT, TF>(kr, me, sx, sy, d, thr, thr_ok)) { is_dead = true; break; }
+                    int u = 0;
+                    for (int r = 0; r < R; ++r) {
+                        const int i = (r << 5) + lane;
+                        const bool act = i < P;
+                        for (int w = 0; w <= r + kwords; ++w, ++u) {
+                            if ((u % SW_WARPS) != warp || !act) continue;
+                            const int cls = ck_cls(ks[p0 + i]);
+                            const SBox<float> me = cbox[p0 + i];
+                            if (w <= r) {
+                                // earlier candidates of the panel with the same class, word w
+                                unsigned rem = cm[(size_t)cls * SW_PW + w];
+                                if (w == r) rem &= lt;
+                                unsigned sw = 0;
+                                for (; rem; rem &= rem - 1) {
+                                    const int bit = __ffs(rem) - 1;
+                                    const SBox<float> ob = cbox[p0 + (w << 5) + bit];
+                                    if (f32) {
+                                        const int rr = pair_f32(me, ob, thr_lo, thr_hi);
+                                        if (rr == 0) continue;
+                                        if (rr == 1) { sw |= 1u << bit; continue; }
+                                    } else if (screen && raw_disjoint(me, ob)) continue;
+                                    if (decide_pair<float, IouT, TF>(ob, me, sx, sy, d, thr, thr_ok)) sw |= 1u << bit;
+                                }
+                                sup[w][i] = sw;
+                            } else {
+                                // kept boxes of the same class, word w - r - 1 of the keep list
+                                const int kw = w - r - 1;
+                                bool is_dead = false;
+                                for (unsigned rem = km[(size_t)cls * SW_KW + kw]; rem; rem &= rem - 1) {
+                                    const int k = (kw << 5) + __ffs(rem) - 1;
+                                    const SBox<float> kr = kraw[k];
+                                    if (f32) {
+                                        const int rr = pair_f32(me, kr, thr_lo, thr_hi);
+                                        if (rr == 0) continue;
+                                        if (rr == 1) { is_dead = true; break; }
+                                    } else if (screen && raw_disjoint(me, kr)) continue;
+                                    if (decide_pair<float, IouT, TF>(kr, me, sx, sy, d, thr, thr_ok)) { is_dead = true; break; }
+                                }
+                                if (is_dead) atomicOr(&dead[r], 1u << lane);
+                            }
                         }
-                    }
-                    if (is_dead) { atomicOr(&dead[i >> 5], 1u << (i & 31)); continue; }
-                    // (b) earlier candidates of the panel with the same class
-                    const int wi = i >> 5;
-                    for (int w = 0; w <= wi; ++w) {
-                        unsigned rem = cm[(size_t)cls * SW_PW + w];
-                        if (w == wi) rem &= (1u << (i & 31)) - 1u;
-                        unsigned sw = 0;
-                        for (; rem; rem &= rem - 1) {
-                            const int bit = __ffs(rem) - 1;
-                            const SBox<float> ob = cbox[p0 + (w << 5) + bit];
-                            if (f32) {
-                                const int r = pair_f32(me, ob, thr_lo, thr_hi);
-                                if (r == 0) continue;
-                                if (r == 1) { sw |= 1u << bit; continue; }
-                            } else if (screen && raw_disjoint(me, ob)) continue;
-                            if (decide_pair<float, IouT, TF>(ob, me, sx, sy, d, thr, thr_ok)) sw |= 1u << bit;
-                        }
-                        sup[w][i] = sw;
                     }
                 }
                 __syncthreads();
@@ -1461,7 +1519,7 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                             keptm = __ballot_sync(0xffffffffu, mine);
                             if (mine) {
                                 const int pos = nk + __popc(keptm & lt);
-                                const unsigned long long key = kB[p0 + i];
+                                const unsigned long long key = ks[p0 + i];
                                 const int cls = ck_cls(key);
                                 kraw[pos] = cbox[p0 + i];
                                 kcls[pos] = (unsigned char)cls;
