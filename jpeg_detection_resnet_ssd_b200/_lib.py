@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libssdcodec.so')
+LIB_PATH = os.environ.get('SSDC_LIB_PATH') or os.path.join(_HERE, 'lib', 'libssdcodec.so')      # (override: A/B builds)
 
 # ---- constants mirrored from include/ssdcodec.h ------------------------------
 OK, ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_DEGENERATE, ERR_NODEVICE, ERR_STATE = 0, -1, -2, -3, -4, -5, -6

@@ -211,11 +211,9 @@ __device__ __forceinline__ void floor_update(FloorSlot* fs, int b, int target, f
 }
 
 // Image-sweep variant of the tile filter (float32, per-class semantics, composite keys, one list per image).
-// A warp-tile with many candidates (the floor has not caught up with the image yet: its first tiles) is filtered
-// twice: the candidates are counted into the histogram first, the floor is raised on the spot, and only what is
-// still above it is emitted - counted-but-dropped candidates lie below the floor, where the histogram is not
-// trusted anyway, and they are real candidates of the image, so the floor stays a valid bound.
-constexpr int D1_DENSE = 64;                  // candidates per warp-tile from which the floor is raised before emitting
+// (Measured and dropped: filtering a crowded warp-tile twice - histogram first, raise the floor on the spot, emit only what
+// is still above it.  It saves a few thousand keys per image at the start of every image and costs more instructions than
+// those keys: SSD512 / conf 0.001: 1.39 M -> 1.57 M images/s without it, SSD300 dense 3.2 M -> 3.9 M.)
 __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst, int rows, int b, int a0,
                                                    const DecodeArgs& g, float thr, int* __restrict__ seg_count,
                                                    unsigned long long* __restrict__ gkeys, PendingKeys* pk,
@@ -227,36 +225,27 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
     const int a = a0 + tid;
     // (the slot's threshold is raised concurrently by other warps: one lane reads it, so that the whole warp filters -
     // and branches - on the same value)
-    float t = fs ? __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0) : thr;
+    const float t = fs ? __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0) : thr;
     int counted = 0;                          // candidates added to the histogram by this call (warp-uniform)
     // ssd_output_decoder.py:207-209, 32 classes per pass
     for (int c0 = 0; c0 < NS; c0 += 32) {
         const int nc = min(32, NS - c0);
         unsigned mask = 0;
-        for (int c = 0; c < nc; ++c) mask |= (unsigned)(row[1 + c0 + c] > t) << c;
+        {
+            // (four classes per trip: the per-class compare is the kernel's base load - one shared-memory read, one
+            // compare, one bit insert; the loop bookkeeping must not double it)
+            const float* cf = row + 1 + c0;
+            int c = 0;
+#pragma unroll 1
+            for (; c + 4 <= nc; c += 4) {
+                const float v0 = cf[c], v1 = cf[c + 1], v2 = cf[c + 2], v3 = cf[c + 3];
+                mask |= ((unsigned)(v0 > t) | ((unsigned)(v1 > t) << 1) | ((unsigned)(v2 > t) << 2) | ((unsigned)(v3 > t) << 3)) << c;
+            }
+            for (; c < nc; ++c) mask |= (unsigned)(cf[c] > t) << c;
+        }
         if (!valid) mask = 0;
         int total = __reduce_add_sync(0xffffffffu, __popc(mask));
         if (total == 0) continue;
-        bool in_hist = false;
-        if (fs && total >= D1_DENSE) {
-            for (unsigned mm = mask; mm; mm &= mm - 1)
-                atomicAdd(&fs->hist[floor_bin_of_ord(ord32(row[1 + c0 + __ffs(mm) - 1]))], 1u);
-            in_hist = true;
-            if (lane == 0) atomicAdd(&fs->since, (unsigned)total);
-            __syncwarp();
-            floor_update(fs, b, g.floor_target, thr, g_floor);
-            __syncwarp();
-            const float t2 = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0);
-            if (t2 > t) {
-                t = t2;
-                for (unsigned mm = mask; mm; mm &= mm - 1) {
-                    const int c = __ffs(mm) - 1;
-                    if (!(row[1 + c0 + c] > t)) mask &= ~(1u << c);
-                }
-                total = __reduce_add_sync(0xffffffffu, __popc(mask));
-                if (total == 0) continue;
-            }
-        }
         // keys carry the class: [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one slot reservation per warp
         const int cnt = __popc(mask);
         int incl = cnt;
@@ -285,13 +274,13 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
             const unsigned ord = ord32(row[1 + c0 + c]);
             *ck++ = ((unsigned long long)ord << 32) | ((unsigned long long)(0xffu - (unsigned)(c0 + c + 1)) << 24) |
                     (unsigned long long)(0xffffffu - (unsigned)a);
-            if (fs && !in_hist) atomicAdd(&fs->hist[floor_bin_of_ord(ord)], 1u);
+            if (fs) atomicAdd(&fs->hist[floor_bin_of_ord(ord)], 1u);
         }
         if (park) {
             __syncwarp();
             pk->n_cur += total; pk->b_cur = b;
         }
-        if (!in_hist) counted += total;
+        counted += total;
     }
     if (fs && counted) {
         unsigned old = 0;
