@@ -955,7 +955,46 @@ def extra_numbers(ctx, _lib, peak):
         out['voc_match_predictions'] = voc_numbers(ctx)
     except Exception as exc:
         out['voc_match_predictions'] = {'error': repr(exc)[:200]}
+    try:
+        out['evaluator_records_from_device'] = records_numbers(ctx, _lib)
+    except Exception as exc:
+        out['evaluator_records_from_device'] = {'error': repr(exc)[:200]}
     return out
+
+
+def records_numbers(ctx, _lib):
+    """the Evaluator's result records (inverse transforms + rounding, average_precision_evaluator.py
+    :402-422) taken from the device-resident rows of a 1024-image decode (`Evaluator.add_decoded_batch`) against the
+    reference's per-detection Python loop (oracle port) on the same detections."""
+    from oracle import eval_prep_oracle as ep
+    from jpeg_detection_resnet_ssd_b200.data_generator import object_detection_2d_misc_utils as mu
+    from jpeg_detection_resnet_ssd_b200.eval_utils.average_precision_evaluator import Evaluator
+    from jpeg_detection_resnet_ssd_b200.ssd_encoder_decoder.ssd_output_decoder import decode_detections
+    cfg = dict(CONFIGS[2], id=2)
+    B = 1024
+    y, _ = synth_decode_input(dict(cfg, unique=64), B, 777, True, 8.0)
+    dec = decode_detections(y, cfg['conf'], cfg['iou'], cfg['top_k'], 'centroids', True, 300, 300)
+
+    class DS(object):
+        pass
+    ds = DS()
+    ds.image_ids, ds.eval_neutral, ds.labels = ['%06d' % i for i in range(B)], None, [np.zeros((0, 5)) for _ in range(B)]
+    inv = [[mu.ResizeInverter(375, 500, 300, 300)] for _ in range(B)]
+    ev = Evaluator(model=None, n_classes=20, data_generator=ds)
+    ev.add_decoded_batch(ds.image_ids, inverse_transforms=inv)
+    ev.reset_predictions()
+    t0 = time.perf_counter()
+    n = ev.add_decoded_batch(ds.image_ids, inverse_transforms=inv)
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rows = ep.apply_inverse_transforms(dec, [[ep.resize_inverter(375, 500, 300, 300)] for _ in range(B)])
+    rec = ep.evaluation_records(rows, False)
+    t_cpu = time.perf_counter() - t0
+    same = bool(np.array_equal(rec[1], ev._acc['cls'][0]) and np.array_equal(rec[2], ev._acc['conf'][0]) and np.array_equal(rec[3], ev._acc['box'][0]))
+    return {'detections': int(n), 'device_path_ms': t_dev * 1e3, 'detections_per_s': n / t_dev, 'cpu_port_ms': t_cpu * 1e3,
+            'cpu_port_detections_per_s': n / t_cpu, 'identical_records': same,
+            'note': 'device path = Evaluator.add_decoded_batch on the rows decode_detections left in HBM (Resize inverter, rounding, float32 '
+                    'records, D2H); cpu port = apply_inverse_transforms + the per-detection loop of the reference on the host results'}
 
 
 def loss_numbers(ctx, _lib, peak):
