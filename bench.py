@@ -955,11 +955,40 @@ def extra_numbers(ctx, _lib, peak):
         out['voc_match_predictions'] = voc_numbers(ctx)
     except Exception as exc:
         out['voc_match_predictions'] = {'error': repr(exc)[:200]}
+    # the other single-GPU BASELINE configurations, device-timed in this process (their full lines - roofline, cpu_baseline,
+    # e2e, parity gate - come from `bench.py --config N`; profiles/r02_bench_c*.json)
+    for c in (0, 1, 3):
+        try:
+            out['config%d_device_timed' % c] = other_config_numbers(ctx, _lib, c)
+        except Exception as exc:
+            out['config%d_device_timed' % c] = {'error': repr(exc)[:200]}
     try:
         out['evaluator_records_from_device'] = records_numbers(ctx, _lib)
     except Exception as exc:
         out['evaluator_records_from_device'] = {'error': repr(exc)[:200]}
     return out
+
+
+def other_config_numbers(ctx, _lib, c):
+    cfg = dict(CONFIGS[c], id=c)
+
+    class A(object):
+        bg_bias = None
+    wl = WORKLOADS[cfg['kind']](cfg, A(), ctx, _lib, 0, 1, cfg['batch'])
+    try:
+        for _ in range(5):
+            wl.step()
+        ctx.synchronize()
+        steps = 20
+        ctx.timer_start()
+        for _ in range(steps):
+            wl.step()
+        ms = ctx.timer_stop()
+        return {'workload': cfg['workload'], 'images_per_s': cfg['batch'] * steps / (ms / 1e3), 'ms_per_step': ms / steps,
+                'l2_policy': wl.l2_note()}
+    finally:
+        ctx.synchronize()
+        wl.free()
 
 
 def records_numbers(ctx, _lib):
