@@ -9,9 +9,10 @@ image.  The inverters the reference's own transformations hand out are affine ma
     (two more)             ...patch_sampling_ops.py:577, :730                  identity
 
 They are recognised (by their closure, or given as the descriptor objects below) and the whole batch is transformed
-by ONE kernel (`ssdc_inverse_transform_rows`, csrc/evalprep.cu).  Any other callable is arbitrary user code: it is
-called on the host exactly as the reference does.  Float64 predictions only go to the device (what
-`decode_detections` returns; the arithmetic is float64 like numpy's); other dtypes take the callables' own path.
+by ONE kernel (`ssdc_inverse_transform_rows`, csrc/evalprep.cu).  Any other callable is arbitrary user code that no
+library can run on the device: it is called exactly as the reference calls it.  Float64 predictions go to the device
+(what `decode_detections` returns; the arithmetic is float64 like numpy's); for other dtypes (the float32 output of the
+Keras layer) the reference's closures are called as they are, which keeps their float32 arithmetic.
 """
 from __future__ import division
 
@@ -25,10 +26,21 @@ except ImportError:
 _DEFAULT_COLS = (2, 3, 4, 5)          # xmin, ymin, xmax, ymax of a prediction row [class, conf, xmin, ymin, xmax, ymax]
 
 
-class ResizeInverter(object):
+class _AffineInverter(object):
+    """An inverter as data.  Calling it on a single `(k, n)` float64 label array runs the same device kernel as
+    `apply_inverse_transforms` (there is no host arithmetic behind these objects)."""
+
+    def __call__(self, labels):
+        labels = np.asarray(labels)
+        if labels.dtype != np.float64 or labels.ndim != 2:
+            raise TypeError("inverter descriptors take (k, n) float64 label arrays (what decode_detections returns); "
+                            "for other dtypes use the closure the reference's transformation returned")
+        return apply_inverse_transforms([labels], [[self]])[0]
+
+
+class ResizeInverter(_AffineInverter):
     """The inverter `Resize(height, width)(image, return_inverter=True)` returns, as data: boxes predicted on the
-    `out_height` x `out_width` image back to the `img_height` x `img_width` original.  Callable like the original
-    (numpy, on the host) so that it can also stand in for it elsewhere."""
+    `out_height` x `out_width` image back to the `img_height` x `img_width` original."""
     kind = 1
 
     def __init__(self, img_height, img_width, out_height, out_width, cols=_DEFAULT_COLS):
@@ -36,15 +48,8 @@ class ResizeInverter(object):
         self.a_x = img_width / out_width
         self.cols = tuple(cols)
 
-    def __call__(self, labels):
-        x0, y0, x1, y1 = self.cols
-        labels = np.copy(labels)
-        labels[:, [y0, y1]] = np.round(labels[:, [y0, y1]] * self.a_y, decimals=0)
-        labels[:, [x0, x1]] = np.round(labels[:, [x0, x1]] * self.a_x, decimals=0)
-        return labels
 
-
-class TranslateInverter(object):
+class TranslateInverter(_AffineInverter):
     """The inverter of the patch samplers: boxes inside a patch back to the image the patch was cut from."""
     kind = 2
 
@@ -52,13 +57,6 @@ class TranslateInverter(object):
         self.a_y = patch_ymin
         self.a_x = patch_xmin
         self.cols = tuple(cols)
-
-    def __call__(self, labels):
-        x0, y0, x1, y1 = self.cols
-        labels = np.copy(labels)
-        labels[:, [y0, y1]] += self.a_y
-        labels[:, [x0, x1]] += self.a_x
-        return labels
 
 
 def describe_inverter(fn):

@@ -132,3 +132,14 @@ def test_box_filter_and_image_validator_match_reference(ctx):
         ImageValidator(n_boxes_min=0)
     with pytest.raises(ValueError):
         BoundGenerator(sample_space=((0.5, 0.1),))
+
+
+def test_inverter_descriptors_are_device_callables(ctx):
+    inp = cases.build_evalprep_input()
+    g = load_golden('evalprep')
+    p = inp['preds'][0]
+    n0 = ctx.launch_count()
+    out = mu.ResizeInverter(*inp['specs'][0][0][1:])(p)
+    assert ctx.launch_count() == n0 + 1 and np.array_equal(out, g['inv_0'])
+    with pytest.raises(TypeError):
+        mu.TranslateInverter(1, 2)(p.astype(np.float32))
