@@ -1431,14 +1431,17 @@ sweep_kernel(unsigned long long* __restrict__ keys, const int* __restrict__ img_
                 {
                     const int R = (P + 31) >> 5;
                     const int kwords = (nkept + 31) >> 5;
-                    int u = 0;
+                    int ubase = 0;                                  // units of the rows before r
                     for (int r = 0; r < R; ++r) {
                         const int i = (r << 5) + lane;
                         const bool act = i < P;
-                        for (int w = 0; w <= r + kwords; ++w, ++u) {
-                            if ((u % SW_WARPS) != warp || !act) continue;
-                            const int cls = ck_cls(ks[p0 + i]);
-                            const SBox<float> me = cbox[p0 + i];
+                        const int nu = r + 1 + kwords;              // units of row r; this warp takes ubase + w == warp (mod SW_WARPS)
+                        const int w0 = (warp - ubase) & (SW_WARPS - 1);
+                        ubase += nu;
+                        if (!act) continue;
+                        const int cls = ck_cls(ks[p0 + i]);
+                        const SBox<float> me = cbox[p0 + i];
+                        for (int w = w0; w < nu; w += SW_WARPS) {
                             if (w <= r) {
                                 // earlier candidates of the panel with the same class, word w
                                 unsigned rem = cm[(size_t)cls * SW_PW + w];
