@@ -499,3 +499,36 @@ def test_pipelined_device_decodes(ctx):
         ctx.synchronize()
         for dd in d:
             ctx.dev_free(dd)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_sweep_vs_general_pipeline_randomised(seed, ctx):
+    """Random candidate densities, thresholds, top_k (1 .. 256), box spreads and floor settings: the image sweep (score
+    floor, histogram selection, bin sort, panel NMS, rescan) and the general per-class pipeline return identical rows."""
+    rng = np.random.default_rng(1000 + seed)
+    layout = ['ssd300', 'tiny', 'ssd300', 'ssd512', 'tiny', 'ssd300'][seed]
+    enc = synth.make_encoder(SSDInputEncoder, layout)
+    kw = synth.layout_kwargs(layout)
+    C = kw['n_classes'] + 1
+    bias = float(rng.uniform(2.0, 9.0)) if layout != 'tiny' else float(rng.uniform(0.0, 2.0))
+    sigma = float(rng.choice([0.01, 0.1, 0.5]))
+    thr = float(rng.choice([0.001, 0.01, 0.05, 0.3]))
+    iou = float(rng.choice([0.1, 0.45, 0.8]))
+    y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 2, 500 + seed, bg_bias=bias, hot=int(rng.integers(0, 80)), offset_sigma=sigma)
+    if seed % 2 == 0:
+        y[0, :, 1:] = np.round(y[0, :, 1:] * 64) / 64                  # score ties: crowded bins, sorting-network fallback
+    y = np.ascontiguousarray(np.tile(y, (int(rng.integers(1, 14)), 1, 1)))
+    tail = ('centroids', True, kw['img_height'], kw['img_width'], str(rng.choice(['half', 'include', 'exclude'])))
+    for top_k in (1, int(rng.integers(2, 60)), 200, 256):
+        ctx.set_option('no_sweep', 1)
+        try:
+            want = product_rows7(*_lib.run_decode(y, _lib.MODE_PER_CLASS, thr, iou, top_k, *tail, ctx=ctx))
+        finally:
+            ctx.set_option('no_sweep', 0)
+        for target in (1, 0):
+            ctx.set_option('floor_target', target)
+            try:
+                got = product_rows7(*_lib.run_decode(y, _lib.MODE_PER_CLASS, thr, iou, top_k, *tail, ctx=ctx))
+            finally:
+                ctx.set_option('floor_target', 0)
+            assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), (seed, top_k, target, bias, sigma, thr, iou)
