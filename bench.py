@@ -92,6 +92,8 @@ def parse_args():
     ap.add_argument('--sustain-ms', type=float, default=200.0)
     ap.add_argument('--floor-target', type=int, default=None, help='diagnosis: SSDC_OPT_FLOOR_TARGET of the context')
     ap.add_argument('--no-pipeline', type=int, default=None, help='diagnosis: SSDC_OPT_NO_PIPELINE of the context')
+    ap.add_argument('--enc-lanes', type=int, default=None, help='diagnosis: SSDC_OPT_ENC_LANES of the context')
+    ap.add_argument('--d1-ctas', type=int, default=None, help='diagnosis: SSDC_OPT_D1_CTAS of the context')
     ap.add_argument('--sync-steps', action='store_true', help='diagnosis: synchronise after every warm-up step')
     return ap.parse_args()
 
@@ -823,6 +825,10 @@ def main():
         ctx.set_option('floor_target', args.floor_target)
     if args.no_pipeline is not None:
         ctx.set_option('no_pipeline', args.no_pipeline)
+    if args.enc_lanes is not None:
+        ctx.set_option('enc_lanes', args.enc_lanes)
+    if args.d1_ctas is not None:
+        ctx.set_option('d1_ctas', args.d1_ctas)
 
     batch, scaling = job_batch(args, cfg)
     if scaling == 'strong':

@@ -96,7 +96,10 @@ int  ssdc_synchronize(ssdc_ctx* ctx);
                                          filtered (D1) while the next one is in flight; 0 = default (64), <0 = one copy */
 #define SSDC_OPT_NO_PIPELINE       7  /* 1: the sweep of a device-resident image-sweep decode runs on the main stream (no overlap
                                          with D1 of the next decode)                                                   */
-#define SSDC_OPT_COUNT             8
+#define SSDC_OPT_ENC_LANES         8  /* device-output encodes (ssdc_encode, on_device != 0) run on this many lanes - stream pair +
+                                         scratch each - so consecutive calls overlap; 0 = default (3), 1 = main stream only     */
+#define SSDC_OPT_D1_CTAS           9  /* resident D1 CTAs per SM (TMA loader); 0 = default                                     */
+#define SSDC_OPT_COUNT             10
 int     ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value);
 int64_t ssdc_get_option(const ssdc_ctx* ctx, int option);
 
@@ -240,7 +243,10 @@ int64_t ssdc_encoder_bad_image(const ssdc_encoder* enc);
  * the `diagnostics=True` copy y_matched (:412-416) and match_idx (B, A) int32:
  * matched ground-truth row, -1 background, -2 neutral.  `on_device != 0`: the
  * three output pointers are device pointers on dev_slot 0 and the call only
- * enqueues work. */
+ * enqueues work: consecutive such calls run beside one another (SSDC_OPT_ENC_LANES;
+ * calls whose outputs overlap are ordered), every other entry point of the library
+ * that touches device memory (ssdc_decode_submit, ssdc_ssd_loss, ssdc_memcpy_*,
+ * ssdc_synchronize, ssdc_timer_*) runs behind them. */
 int ssdc_encode(ssdc_encoder* enc, const double* gt, const int64_t* gt_offsets, int64_t B,
                 int on_device, double* y_encoded, double* y_matched, int32_t* match_idx);
 

@@ -105,6 +105,7 @@ void ssdc_destroy(ssdc_ctx* ctx) {
         if (d.stream2) cudaStreamSynchronize(d.stream2);
         if (d.stream_nms) cudaStreamSynchronize(d.stream_nms);
         if (d.stream) cudaStreamSynchronize(d.stream);
+        d.lanes_release();
         Buf* sb[] = {&d.shadow.ints, &d.shadow.keys, &d.shadow.hist, &d.shadow.pad_rows, &d.shadow.pad_anchor, &d.shadow.out_count};
         for (Buf* b : sb) b->release();
         for (int k = 0; k < 2; ++k) { if (d.ev_d1[k]) cudaEventDestroy(d.ev_d1[k]); if (d.ev_sweep[k]) cudaEventDestroy(d.ev_sweep[k]); }
@@ -135,6 +136,7 @@ int ssdc_synchronize(ssdc_ctx* ctx) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (DevCtx& d : ctx->devs) {
         SSDC_CUDA(cudaSetDevice(d.device));
+        SSDC_TRY(d.wait_encodes());
         SSDC_CUDA(cudaStreamSynchronize(d.stream));
         SSDC_CUDA(cudaStreamSynchronize(d.stream_nms));
         d.sweep_pending[0] = d.sweep_pending[1] = false;
@@ -192,6 +194,8 @@ int ssdc_timer_start(ssdc_ctx* ctx) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (DevCtx& d : ctx->devs) {
         SSDC_CUDA(cudaSetDevice(d.device));
+        SSDC_TRY(d.wait_sweeps());                       // the span starts when the work in flight on the side streams has ended
+        SSDC_TRY(d.wait_encodes());
         SSDC_CUDA(cudaEventRecord(d.t0, d.stream));
     }
     return SSDC_OK;
@@ -204,6 +208,7 @@ int ssdc_timer_stop(ssdc_ctx* ctx, double* elapsed_ms) {
     for (DevCtx& d : ctx->devs) {
         SSDC_CUDA(cudaSetDevice(d.device));
         SSDC_TRY(d.wait_sweeps());                       // the span ends when the sweeps on the side stream have ended too
+        SSDC_TRY(d.wait_encodes());                      // ... and the encodes on their lanes
         SSDC_CUDA(cudaEventRecord(d.t1, d.stream));
     }
     for (DevCtx& d : ctx->devs) {
@@ -249,6 +254,7 @@ int ssdc_memcpy_h2d(ssdc_ctx* ctx, int dev_slot, void* dst, const void* src, uin
     DevCtx* d = slot(ctx, dev_slot);
     if (!d) return SSDC_ERR_ARG;
     SSDC_CUDA(cudaSetDevice(d->device));
+    SSDC_TRY(d->wait_encodes());
     SSDC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
     SSDC_CUDA(cudaStreamSynchronize(d->stream));
     return SSDC_OK;
@@ -257,6 +263,7 @@ int ssdc_memcpy_d2h(ssdc_ctx* ctx, int dev_slot, void* dst, const void* src, uin
     DevCtx* d = slot(ctx, dev_slot);
     if (!d) return SSDC_ERR_ARG;
     SSDC_CUDA(cudaSetDevice(d->device));
+    SSDC_TRY(d->wait_encodes());
     SSDC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream));
     SSDC_CUDA(cudaStreamSynchronize(d->stream));
     return SSDC_OK;

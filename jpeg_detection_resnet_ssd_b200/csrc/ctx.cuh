@@ -175,6 +175,68 @@ struct DevCtx {
     // encode scratch
     Buf gt, gt_off, partial, matches, enc_out, enc_out2, enc_idx, enc_flags;
     size_t cand_clean = 0;           // leading bytes of `matches` known to hold -1 (the sparse path's decision array between calls)
+    // Pipelining of consecutive device-output encodes (ssdc_encode with on_device = 1 only enqueues work): call i runs on
+    // lane i % ENC_LANES - its own stream pair, events and scratch - so the latency chain of one call (upload, seed, pair,
+    // greedy rounds, patch) runs beside the chains of its neighbours and beside their template streams.  A lane starts
+    // behind everything enqueued on `stream` before the call; `stream` (and with it every other entry point of the
+    // library) waits for the lanes still in flight through wait_encodes().
+    static constexpr int ENC_LANES = 3;
+    struct EncLane {
+        cudaStream_t st = nullptr, ts = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
+        Buf gt, partial, matches;
+        size_t cand_clean = 0;
+        bool pending = false;
+        const char* out_lo[3] = {nullptr, nullptr, nullptr};      // output ranges of the call in flight (WAW guard between lanes)
+        const char* out_hi[3] = {nullptr, nullptr, nullptr};
+    } enc_lane[ENC_LANES];
+    cudaEvent_t ev_order = nullptr;  // recorded on `stream` at the start of a lane call
+    int enc_next = 0;
+    int lanes_init() {
+        if (ev_order) return SSDC_OK;
+        for (int k = 0; k < ENC_LANES; ++k) {
+            EncLane& L = enc_lane[k];
+            if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&L.ts, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+                set_error("encode lanes: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return SSDC_ERR_CUDA;
+            }
+        }
+        if (cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("encode lanes: event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return SSDC_ERR_CUDA;
+        }
+        return SSDC_OK;
+    }
+    // makes `stream` wait for the encodes still in flight on the lanes
+    int wait_encodes() {
+        for (int k = 0; k < ENC_LANES; ++k) {
+            EncLane& L = enc_lane[k];
+            if (!L.pending) continue;
+            cudaError_t e = cudaStreamWaitEvent(stream, L.ev_done, 0);
+            if (e != cudaSuccess) { set_error("cudaStreamWaitEvent(encode lane) failed: %s", cudaGetErrorString(e)); return SSDC_ERR_CUDA; }
+            L.pending = false;
+        }
+        return SSDC_OK;
+    }
+    void lanes_release() {
+        for (int k = 0; k < ENC_LANES; ++k) {
+            EncLane& L = enc_lane[k];
+            if (L.st) cudaStreamSynchronize(L.st);
+            if (L.ts) cudaStreamSynchronize(L.ts);
+            L.gt.release(); L.partial.release(); L.matches.release();
+            if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+            if (L.ev_join) cudaEventDestroy(L.ev_join);
+            if (L.ev_done) cudaEventDestroy(L.ev_done);
+            if (L.ts) cudaStreamDestroy(L.ts);
+            if (L.st) cudaStreamDestroy(L.st);
+            L = EncLane();
+        }
+        if (ev_order) { cudaEventDestroy(ev_order); ev_order = nullptr; }
+    }
     // thin ops scratch
     Buf t0buf, t1buf, t2buf, t3buf;
 };

@@ -1952,6 +1952,7 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
                             2 * sizeof(FloorSlot);
         int ctas_per_sm = (int)((226 * 1024) / (smem + 1024 + 256));
         if (ctas_per_sm > max_ctas_per_sm) ctas_per_sm = max_ctas_per_sm;
+        if (ctx->opt[SSDC_OPT_D1_CTAS] > 0 && ctx->opt[SSDC_OPT_D1_CTAS] < ctas_per_sm) ctas_per_sm = (int)ctx->opt[SSDC_OPT_D1_CTAS];
         if (ctas_per_sm < 1) ctas_per_sm = 1;
 #ifdef SSDC_TIMING_KNOBS
         if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only; not in release builds)
@@ -2366,6 +2367,7 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     // for the sweep that used it two decodes ago; everything else waits for every sweep still in flight (it shares the
     // current bank, or overwrites the staged input the sweep decodes its boxes from)
     const bool pipe = g.sweep && on_device && !ctx->profile && ctx->opt[SSDC_OPT_NO_PIPELINE] == 0;
+    if (on_device) SSDC_TRY(d->wait_encodes());            // (the input may be what an encode still in flight on a lane writes)
     if (pipe) { d->swap_banks(); SSDC_TRY(d->wait_sweeps(d->bank)); }
     else SSDC_TRY(d->wait_sweeps());
     const size_t nseg = (size_t)g.nseg;

@@ -1609,7 +1609,15 @@ struct GtUpload {
     int* zeros = nullptr;                  // n_gt + B + 1 ints, zero
     GtPrep* gtp = nullptr;                 // n_gt prepared rows (written on the device)
 };
-static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, GtUpload* up) {
+// Streams, events and scratch of one encode call: the device's own (synchronous host-output calls, profiling) or those of
+// an encode lane (device-output calls, DevCtx::EncLane).
+struct EncRes {
+    cudaStream_t st, ts;
+    cudaEvent_t ev_fork, ev_join;
+    Buf* gt; Buf* partial; Buf* matches;
+    size_t* cand_clean;
+};
+static int upload_gt(DevCtx* d, const EncRes& R, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B, GtUpload* up) {
     const int64_t first = gt_offsets[b0], last = gt_offsets[b0 + B];
     const int64_t n = last - first;
     up->n_gt = n;
@@ -1626,18 +1634,69 @@ static int upload_gt(DevCtx* d, const double* gt, const int64_t* gt_offsets, int
     for (int64_t i = 0; i <= B; ++i) ho[i] = gt_offsets[b0 + i] - first;
     if (n > 0) memcpy(h + off_bytes, gt + first * 5, (size_t)n * 5 * sizeof(double));
     memset(h + off_bytes + gt_bytes, 0, z_bytes);
-    SSDC_TRY(d->gt.ensure(copy_bytes + (size_t)n * sizeof(GtPrep)));
-    char* dv = d->gt.as<char>();
-    SSDC_CUDA(cudaMemcpyAsync(dv, h, copy_bytes, cudaMemcpyHostToDevice, d->stream));
+    SSDC_TRY(R.gt->ensure(copy_bytes + (size_t)n * sizeof(GtPrep)));
+    char* dv = R.gt->as<char>();
+    SSDC_CUDA(cudaMemcpyAsync(dv, h, copy_bytes, cudaMemcpyHostToDevice, R.st));
     up->gt_off = reinterpret_cast<const long long*>(dv);
     up->rows = reinterpret_cast<const double*>(dv + off_bytes);
     up->zeros = reinterpret_cast<int*>(dv + off_bytes + gt_bytes);
     up->gtp = n > 0 ? reinterpret_cast<GtPrep*>(dv + copy_bytes) : nullptr;
-    return d->stage_done(hs, d->stream);
+    return d->stage_done(hs, R.st);
 }
 
+static int encode_body(ssdc_encoder* enc, int slot, const EncRes& R, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B,
+                       int max_m, double* y_dev, double* y2_dev, int* midx_dev);
+
+// `lanes`: the call only enqueues work (device-resident outputs) and may run beside its neighbours on an encode lane.
 int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B,
-               int max_m, double* y_dev, double* y2_dev, int* midx_dev) {
+               int max_m, double* y_dev, double* y2_dev, int* midx_dev, bool lanes) {
+    ssdc_ctx* ctx = enc->ctx;
+    DevCtx* d = &ctx->devs[slot];
+    SSDC_CUDA(cudaSetDevice(d->device));
+    if (B == 0) return SSDC_OK;
+    int n_lanes = (int)ctx->opt[SSDC_OPT_ENC_LANES];
+    if (n_lanes <= 0 || n_lanes > DevCtx::ENC_LANES) n_lanes = DevCtx::ENC_LANES;
+    if (!lanes || ctx->profile || n_lanes == 1) {
+        SSDC_TRY(d->wait_encodes());
+        EncRes R = {d->stream, d->stream2, d->ev_fork, d->ev_join, &d->gt, &d->partial, &d->matches, &d->cand_clean};
+        return encode_body(enc, slot, R, gt, gt_offsets, b0, B, max_m, y_dev, y2_dev, midx_dev);
+    }
+    SSDC_TRY(d->lanes_init());
+    if (d->enc_next >= n_lanes) d->enc_next = 0;
+    const int li = d->enc_next;
+    d->enc_next = (li + 1) % n_lanes;
+    DevCtx::EncLane& L = d->enc_lane[li];
+    // behind everything the main stream holds so far (a reader of the output buffers, an earlier synchronous call) and
+    // behind the sweeps in flight (they read their decode's input)
+    SSDC_CUDA(cudaEventRecord(d->ev_order, d->stream));
+    SSDC_CUDA(cudaStreamWaitEvent(L.st, d->ev_order, 0));
+    for (int k = 0; k < 2; ++k)
+        if (d->sweep_pending[k]) SSDC_CUDA(cudaStreamWaitEvent(L.st, d->ev_sweep[k], 0));
+    // two lanes never write the same bytes at the same time: a call whose outputs overlap those of a call in flight on
+    // another lane runs behind it
+    const size_t img_elems = (size_t)enc->A * (enc->p.n_classes + 12);
+    const char* lo[3] = {reinterpret_cast<const char*>(y_dev), reinterpret_cast<const char*>(y2_dev), reinterpret_cast<const char*>(midx_dev)};
+    const size_t len[3] = {(size_t)B * img_elems * sizeof(double), (size_t)B * img_elems * sizeof(double), (size_t)B * enc->A * sizeof(int)};
+    for (int k = 0; k < DevCtx::ENC_LANES; ++k) {
+        DevCtx::EncLane& O = d->enc_lane[k];
+        if (k == li || !O.pending) continue;
+        bool clash = false;
+        for (int i = 0; i < 3 && !clash; ++i)
+            for (int j = 0; j < 3 && !clash; ++j)
+                clash = lo[i] && O.out_lo[j] && lo[i] < O.out_hi[j] && O.out_lo[j] < lo[i] + len[i];
+        if (clash) SSDC_CUDA(cudaStreamWaitEvent(L.st, O.ev_done, 0));
+    }
+    EncRes R = {L.st, L.ts, L.ev_fork, L.ev_join, &L.gt, &L.partial, &L.matches, &L.cand_clean};
+    const int r = encode_body(enc, slot, R, gt, gt_offsets, b0, B, max_m, y_dev, y2_dev, midx_dev);
+    // (also after a failure: whatever was enqueued must be waited for)
+    if (cudaEventRecord(L.ev_done, L.st) != cudaSuccess) { set_error("cudaEventRecord(encode lane) failed"); return SSDC_ERR_CUDA; }
+    L.pending = true;
+    for (int i = 0; i < 3; ++i) { L.out_lo[i] = lo[i]; L.out_hi[i] = lo[i] ? lo[i] + len[i] : nullptr; }
+    return r;
+}
+
+static int encode_body(ssdc_encoder* enc, int slot, const EncRes& R, const double* gt, const int64_t* gt_offsets, int64_t b0, int64_t B,
+                       int max_m, double* y_dev, double* y2_dev, int* midx_dev) {
     ssdc_ctx* ctx = enc->ctx;
     DevCtx* d = &ctx->devs[slot];
     SSDC_CUDA(cudaSetDevice(d->device));
@@ -1652,7 +1711,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     g.d = (p.border_pixels == SSDC_BORDER_INCLUDE) ? 1.0 : (p.border_pixels == SSDC_BORDER_EXCLUDE ? -1.0 : 0.0);
     g.img_h = p.img_h; g.img_w = p.img_w; g.normalize = p.normalize;
 
-    cudaStream_t st = d->stream;
+    cudaStream_t st = R.st;
     const size_t row_bytes = (size_t)g.W * sizeof(double);
     const bool tma_ok = (reinterpret_cast<uintptr_t>(y_dev) % 16 == 0) && (!y2_dev || reinterpret_cast<uintptr_t>(y2_dev) % 16 == 0) &&
                         (((size_t)enc->A * row_bytes) % 16 == 0) && (((size_t)ET_ROWS * row_bytes) % 16 == 0) &&
@@ -1668,10 +1727,10 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
     if (overlap && dbg != 1) {
         // E3 template stream: independent of the ground truth, so it starts first and runs beside E1 / E2.
         // (With per-launch profiling on, everything stays on the main stream so that each kernel is timed alone.)
-        cudaStream_t ts = ctx->profile ? st : d->stream2;
+        cudaStream_t ts = ctx->profile ? st : R.ts;
         if (ts != st) {
-            SSDC_CUDA(cudaEventRecord(d->ev_fork, st));
-            SSDC_CUDA(cudaStreamWaitEvent(ts, d->ev_fork, 0));
+            SSDC_CUDA(cudaEventRecord(R.ev_fork, st));
+            SSDC_CUDA(cudaStreamWaitEvent(ts, R.ev_fork, 0));
         }
         const int tiles = (int)((enc->A + ET_ROWS - 1) / ET_ROWS);
         int splits = (2 * d->sm_count + tiles - 1) / tiles;
@@ -1683,10 +1742,10 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             template_tma_kernel<<<(unsigned)(tiles * splits), ET_THREADS, smem_tpl, ts>>>(enc->dev[slot].anchor_tail.as<double>(), g, tiles, splits, (int)B, y_dev, y2_dev);
             SSDC_TRY(check_launch("template_tma_kernel"));
         }
-        if (ts != st) SSDC_CUDA(cudaEventRecord(d->ev_join, ts));
+        if (ts != st) SSDC_CUDA(cudaEventRecord(R.ev_join, ts));
     }
     GtUpload up;
-    SSDC_TRY(upload_gt(d, gt, gt_offsets, b0, B, &up));
+    SSDC_TRY(upload_gt(d, R, gt, gt_offsets, b0, B, &up));
     const int64_t n_gt = up.n_gt;
     const long long* gt_off = up.gt_off;
     const Box<double>* abox = enc->dev[slot].anchor_box.as<Box<double>>();
@@ -1709,12 +1768,12 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             // consumes (the position list names exactly the entries that were written), so the 4 bytes per anchor are
             // only cleared once per allocation instead of once per call.
             const size_t need = (size_t)total * sizeof(int);
-            if (need > d->matches.cap) d->cand_clean = 0;
-            SSDC_TRY(d->matches.ensure(need));
-            cand = d->matches.as<int>();
+            if (need > R.matches->cap) *R.cand_clean = 0;
+            SSDC_TRY(R.matches->ensure(need));
+            cand = R.matches->as<int>();
             if (n_gt > 0) {
-                if (d->cand_clean < need) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, d->matches.cap, st));
-                d->cand_clean = 0;          // (dirty until the patch kernel of this call has been enqueued)
+                if (*R.cand_clean < need) SSDC_CUDA(cudaMemsetAsync(cand, 0xff, R.matches->cap, st));
+                *R.cand_clean = 0;          // (dirty until the patch kernel of this call has been enqueued)
             }
         }
         int* plist = nullptr;
@@ -1740,8 +1799,8 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
             const size_t o_lv = carve((size_t)n_gt * EL_CAP * sizeof(double));
             const size_t o_li = carve((size_t)n_gt * EL_CAP * sizeof(int));
             const size_t o_pl = use_plist ? carve((size_t)(total + n_gt) * sizeof(int)) : 0;      // every anchor once + the bipartite matches
-            SSDC_TRY(d->partial.ensure(off));
-            char* base = d->partial.as<char>();
+            SSDC_TRY(R.partial->ensure(off));
+            char* base = R.partial->as<char>();
             match = reinterpret_cast<int*>(base + o_mt);
             int* lcnt = up.zeros;                       // list lengths, irregular flags and the position counter arrive
             int* img_irr = up.zeros + n_gt;             // zeroed with the upload
@@ -1772,13 +1831,13 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
                 SSDC_TRY(check_launch("greedy_kernel"));
             }
         }
-        if (!ctx->profile && dbg != 1) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+        if (!ctx->profile && dbg != 1) SSDC_CUDA(cudaStreamWaitEvent(st, R.ev_join, 0));
         if (n_gt > 0 && dbg != 2) {
             LaunchScope ls(ctx, d, SSDC_K_ENC_PATCH);
             if (plist) {
                 apply_list_kernel<<<(unsigned)(d->sm_count * 8), 128, 0, st>>>(plist, pcount, cand, midx_dev ? 0 : 1, gtp, gt_off, tail, g, y_dev, y2_dev);
                 SSDC_TRY(check_launch("apply_list_kernel"));
-                if (!midx_dev) d->cand_clean = d->matches.cap;
+                if (!midx_dev) *R.cand_clean = R.matches->cap;
             } else {
                 long long blocks = (total + AP_WIN - 1) / AP_WIN;
                 if (blocks > (long long)d->sm_count * 8) blocks = (long long)d->sm_count * 8;
@@ -1797,8 +1856,8 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         size_t o_mt = carve((size_t)n_gt * sizeof(int));
         size_t o_ir = carve((size_t)B * sizeof(int));
         size_t o_rm = carve((size_t)n_gt * sizeof(unsigned long long));
-        SSDC_TRY(d->partial.ensure(off));
-        char* base = d->partial.as<char>();
+        SSDC_TRY(R.partial->ensure(off));
+        char* base = R.partial->as<char>();
         double* part_val = reinterpret_cast<double*>(base + o_pv);
         int* part_idx = reinterpret_cast<int*>(base + o_pi);
         match = reinterpret_cast<int*>(base + o_mt);
@@ -1836,7 +1895,7 @@ int encode_dev(ssdc_encoder* enc, int slot, const double* gt, const int64_t* gt_
         const size_t smem_gt = (size_t)max_m * (sizeof(Box<double>) + sizeof(float4) + sizeof(int)) + 16;
         if (overlap) {
             // patch the rows of matched / neutral anchors once the template has landed
-            if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+            if (!ctx->profile) SSDC_CUDA(cudaStreamWaitEvent(st, R.ev_join, 0));
             if (n_gt == 0 && !midx_dev) return SSDC_OK;
             LaunchScope ls(ctx, d, SSDC_K_ENC_PATCH);
             SSDC_CUDA(cudaFuncSetAttribute(write_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gt));
@@ -1950,6 +2009,8 @@ void ssdc_encoder_destroy(ssdc_encoder* enc) {
     std::lock_guard<std::mutex> lk(enc->ctx->mu);
     for (size_t i = 0; i < enc->dev.size(); ++i) {
         cudaSetDevice(enc->ctx->devs[i].device);
+        enc->ctx->devs[i].wait_encodes();                 // (encodes in flight on the lanes read the tables freed below)
+        cudaStreamSynchronize(enc->ctx->devs[i].stream);
         enc->dev[i].anchor_box.release();
         enc->dev[i].anchor_tail.release();
         enc->dev[i].anchor_boxf.release();
@@ -1997,7 +2058,7 @@ int ssdc_encode(ssdc_encoder* enc, const double* gt, const int64_t* gt_offsets, 
     const size_t img_elems = (size_t)enc->A * (enc->p.n_classes + 12);
     if (on_device) {
         if (n != 1) { set_error("ssdc_encode: device-resident output needs a single-device context"); return SSDC_ERR_ARG; }
-        return encode_dev(enc, 0, gt, gt_offsets, 0, B, max_m, y_encoded, y_matched, match_idx);
+        return encode_dev(enc, 0, gt, gt_offsets, 0, B, max_m, y_encoded, y_matched, match_idx, true);
     }
     for (int i = 0; i < n; ++i) {
         DevCtx& d = ctx->devs[i];
@@ -2009,7 +2070,7 @@ int ssdc_encode(ssdc_encoder* enc, const double* gt, const int64_t* gt_offsets, 
         if (y_matched) SSDC_TRY(d.enc_out2.ensure((size_t)(b1 - b0) * img_elems * sizeof(double)));
         if (match_idx) SSDC_TRY(d.enc_idx.ensure((size_t)(b1 - b0) * enc->A * sizeof(int)));
         SSDC_TRY(encode_dev(enc, i, gt, gt_offsets, b0, b1 - b0, max_m, d.enc_out.as<double>(),
-                            y_matched ? d.enc_out2.as<double>() : nullptr, match_idx ? d.enc_idx.as<int>() : nullptr));
+                            y_matched ? d.enc_out2.as<double>() : nullptr, match_idx ? d.enc_idx.as<int>() : nullptr, false));
         SSDC_CUDA(cudaMemcpyAsync(y_encoded + (size_t)b0 * img_elems, d.enc_out.p, (size_t)(b1 - b0) * img_elems * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
         if (y_matched)
             SSDC_CUDA(cudaMemcpyAsync(y_matched + (size_t)b0 * img_elems, d.enc_out2.p, (size_t)(b1 - b0) * img_elems * sizeof(double), cudaMemcpyDeviceToHost, d.stream));

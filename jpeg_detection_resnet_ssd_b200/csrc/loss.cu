@@ -430,6 +430,7 @@ extern "C" int ssdc_ssd_loss(ssdc_ctx* ctx, const void* y_true, int dtype_true, 
     DevCtx& d = ctx->devs[0];
     SSDC_CUDA(cudaSetDevice(d.device));
     cudaStream_t st = d.stream;
+    if (on_device) SSDC_TRY(d.wait_encodes());             // (y_true may be what an encode still in flight on a lane writes)
     const int W = C + 12;
     const long long n_boxes = B * A;
     const size_t true_bytes = (size_t)n_boxes * W * (dtype_true == SSDC_F32 ? 4 : 8), pred_bytes = (size_t)n_boxes * W * 4;

@@ -228,3 +228,41 @@ def test_back_to_back_device_encodes_keep_their_own_ground_truth(ctx):
         ctx.d2h(got, d)
         assert np.array_equal(got, w)
         ctx.dev_free(d)
+
+
+@pytest.mark.parametrize('lanes', [1, 2, 3])
+def test_device_encodes_on_lanes_are_ordered_where_they_must_be(ctx, lanes):
+    """Device-output encodes run on `enc_lanes` lanes (stream pair + scratch each).  Calls that write the same buffer must
+    land in call order (the later call wins, never a mix of one call's template and another's patches), a reader enqueued
+    behind them (ssdc_memcpy_d2h here) must see the finished result, and a different `match_idx` output per call must
+    stay with its call."""
+    from jpeg_detection_resnet_ssd_b200 import _lib
+    enc = synth.make_encoder(enc_mod.SSDInputEncoder, 'ssd300')
+    _, h = enc._encoder()
+    lib = ctx.lib
+    B, A = 6, 8732
+    n = B * A * 33 * 8
+    batches = [synth.synth_ground_truth(300, 300, 20, B, seed=40 + s, min_boxes=1 + 2 * s, max_boxes=4 + 2 * s) for s in range(7)]
+    want = [enc(gt, return_matches=True) for gt in batches]
+    buf = [ctx.dev_alloc(n) for _ in range(2)]
+    idx = [ctx.dev_alloc(B * A * 4) for _ in batches]
+    target = [0, 0, 1, 0, 1, 1, 0]
+    ctx.set_option('enc_lanes', lanes)
+    try:
+        for _ in range(3):                                    # (repeated: the lanes' scratch is reused while calls are in flight)
+            for gt, t, di in zip(batches, target, idx):
+                f, o = synth.flatten_ground_truth(gt)
+                _lib.check(lib.ssdc_encode(h, _lib.ptr(f), _lib.ptr(o), B, 1, buf[t], None, di))
+        got = np.empty((B, A, 33))
+        for t, last in ((0, 6), (1, 5)):
+            ctx.d2h(got, buf[t])                              # no synchronize in between: the copy itself runs behind the lanes
+            assert np.array_equal(got, want[last][0]), (lanes, t)
+        mi = np.empty((B, A), np.int32)
+        for w, di in zip(want, idx):
+            ctx.d2h(mi, di)
+            assert np.array_equal(mi, w[1])
+    finally:
+        ctx.set_option('enc_lanes', 0)
+        ctx.synchronize()
+        for d in buf + idx:
+            ctx.dev_free(d)
