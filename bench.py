@@ -94,6 +94,7 @@ def parse_args():
     ap.add_argument('--no-pipeline', type=int, default=None, help='diagnosis: SSDC_OPT_NO_PIPELINE of the context')
     ap.add_argument('--enc-lanes', type=int, default=None, help='diagnosis: SSDC_OPT_ENC_LANES of the context')
     ap.add_argument('--d1-ctas', type=int, default=None, help='diagnosis: SSDC_OPT_D1_CTAS of the context')
+    ap.add_argument('--no-l2-hints', type=int, default=None, help='diagnosis: SSDC_OPT_NO_L2_HINTS of the context')
     ap.add_argument('--sync-steps', action='store_true', help='diagnosis: synchronise after every warm-up step')
     return ap.parse_args()
 
@@ -829,6 +830,8 @@ def main():
         ctx.set_option('enc_lanes', args.enc_lanes)
     if args.d1_ctas is not None:
         ctx.set_option('d1_ctas', args.d1_ctas)
+    if args.no_l2_hints is not None:
+        ctx.set_option('no_l2_hints', args.no_l2_hints)
 
     batch, scaling = job_batch(args, cfg)
     if scaling == 'strong':

@@ -97,9 +97,11 @@ int  ssdc_synchronize(ssdc_ctx* ctx);
 #define SSDC_OPT_NO_PIPELINE       7  /* 1: the sweep of a device-resident image-sweep decode runs on the main stream (no overlap
                                          with D1 of the next decode)                                                   */
 #define SSDC_OPT_ENC_LANES         8  /* device-output encodes (ssdc_encode, on_device != 0) run on this many lanes - stream pair +
-                                         scratch each - so consecutive calls overlap; 0 = default (3), 1 = main stream only     */
+                                         scratch each - so consecutive calls overlap; 0 = default (4), 1 = main stream only     */
 #define SSDC_OPT_D1_CTAS           9  /* resident D1 CTAs per SM (TMA loader); 0 = default                                     */
-#define SSDC_OPT_COUNT             10
+#define SSDC_OPT_NO_L2_HINTS       10 /* 1: D1's bulk copies of y_pred carry no L2 eviction hint.  Default: evict_first - the batch
+                                         crosses the L2 once and must not displace the keys / histograms D1 leaves for the sweep */
+#define SSDC_OPT_COUNT             11
 int     ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value);
 int64_t ssdc_get_option(const ssdc_ctx* ctx, int option);
 

@@ -1,5 +1,6 @@
 // ctx.cu - C ABI glue: context lifetime, memory helpers, timing, decode submit/collect.
 #include "ctx.cuh"
+#include <map>
 #include <algorithm>
 
 namespace ssdc {
@@ -19,6 +20,17 @@ int check_launch(const char* what) {
         set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
         return SSDC_ERR_CUDA;
     }
+    return SSDC_OK;
+}
+
+int ensure_dyn_smem(int device, const void* fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> seen;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = seen[std::make_pair(device, fn)];
+    if (bytes <= cur) return SSDC_OK;
+    SSDC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
     return SSDC_OK;
 }
 

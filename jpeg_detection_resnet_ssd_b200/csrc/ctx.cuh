@@ -128,10 +128,10 @@ struct DevCtx {
     Buf pad_rows, pad_anchor;        // image-sweep path: (B, top_k, 6) float64 rows + anchor ids, as the sweep leaves them
     // small pinned staging areas for asynchronous H2D copies of per-call host data: a ring guarded by events, so a
     // call that only enqueues work never overwrites bytes an earlier call's copy has not read yet
-    static constexpr int H_RING = 4;
+    static constexpr int H_RING = 8;
     PinnedBuf h_ring[H_RING];
-    cudaEvent_t h_ev[H_RING] = {nullptr, nullptr, nullptr, nullptr};
-    bool h_busy[H_RING] = {false, false, false, false};
+    cudaEvent_t h_ev[H_RING] = {};
+    bool h_busy[H_RING] = {};
     int h_next = 0;
     // Stages `bytes` of per-call host data: returns a pinned area the caller fills and then copies from with
     // cudaMemcpyAsync on `stream`, followed by staged_done().
@@ -180,7 +180,7 @@ struct DevCtx {
     // greedy rounds, patch) runs beside the chains of its neighbours and beside their template streams.  A lane starts
     // behind everything enqueued on `stream` before the call; `stream` (and with it every other entry point of the
     // library) waits for the lanes still in flight through wait_encodes().
-    static constexpr int ENC_LANES = 3;
+    static constexpr int ENC_LANES = 6;
     struct EncLane {
         cudaStream_t st = nullptr, ts = nullptr;
         cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
@@ -282,6 +282,9 @@ struct LaunchScope {
 };
 
 int check_launch(const char* what);
+// Raises a kernel's dynamic shared-memory limit on `device` when it is below `bytes` (remembered per device and kernel:
+// the hot paths do not pay a driver call per launch for it).
+int ensure_dyn_smem(int device, const void* fn, size_t bytes);
 
 // implemented in decode.cu / encode.cu / thin.cu
 int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, int on_device,

@@ -54,6 +54,7 @@ struct DecodeArgs {
     double iou_thr, sx, sy, d;
     int nseg;
     int sweep;      // per-image candidate lists with composite keys (image sweep path)
+    int evict_first;   // D1's bulk copies carry the L2 evict_first hint
 };
 
 // ---------------------------------------------------------------------------
@@ -448,6 +449,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ... with an L2 eviction-priority hint: the batch is read exactly once, so its lines should be the first to leave the L2
+// (evict_first) instead of displacing the keys, counters and histograms the same kernel writes for the sweep.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -525,6 +538,7 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
         // ---- producer warp (lane 0 issues the copies; the whole warp serves the floor slots) ----
         int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
         int it = 0, armed = -1;
+        const uint64_t pol = g.evict_first ? l2_policy_evict_first() : 0ull;
         for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
             if (tile_id == g.tiles) { tile_id = 0; ++b; }
             const int s = it % D1_STAGES;
@@ -543,7 +557,8 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
                 const int rows = min(g.tile_rows, A - a0);
                 const uint32_t bytes = (uint32_t)((size_t)rows * W * sizeof(InT));
                 mbar_expect_tx(&full[s], bytes);
-                tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
+                if (g.evict_first) tma_load_1d_hint(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s], pol);
+                else tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
             }
             __syncwarp();
         }
@@ -1961,10 +1976,10 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         long long grid = (long long)d->sm_count * ctas_per_sm;
         if (grid > total_tiles) grid = total_tiles;
         if (fast) {
-            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSDC_TRY(ensure_dyn_smem(d->device, (const void*)decode_filter_tma_kernel<InT, true>, smem));
             decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         } else {
-            SSDC_CUDA(cudaFuncSetAttribute(decode_filter_tma_kernel<InT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSDC_TRY(ensure_dyn_smem(d->device, (const void*)decode_filter_tma_kernel<InT, false>, smem));
             decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         }
         SSDC_TRY(check_launch("decode_filter_tma_kernel"));
@@ -2129,12 +2144,12 @@ static int run_sweep(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const HostFeed&
         const bool narrow = B > 3LL * d->sm_count;
         const size_t dyn = (size_t)g.C * ((narrow ? 128 : 256) / 32 + SW_KW) * sizeof(unsigned);
         if (narrow) {
-            SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            SSDC_TRY(ensure_dyn_smem(d->device, (const void*)sweep_kernel<IouT, TF, 128>, dyn));
             sweep_kernel<IouT, TF, 128><<<(unsigned)B, 128, dyn, ns>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
                 g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
         } else {
-            SSDC_CUDA(cudaFuncSetAttribute(sweep_kernel<IouT, TF, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            SSDC_TRY(ensure_dyn_smem(d->device, (const void*)sweep_kernel<IouT, TF, 256>, dyn));
             sweep_kernel<IouT, TF, 256><<<(unsigned)B, 256, dyn, ns>>>(
                 d->keys.as<unsigned long long>(), img_count, (size_t)g.NS * g.A, reinterpret_cast<const float*>(y_dev), g, (float)thr,
                 g_floor, d->hist.as<unsigned>(), ints + L.counters, d->pad_rows.as<double>(), d->pad_anchor.as<int>(), d->out_count.as<int>());
@@ -2352,6 +2367,7 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     if (B == 0) { job.valid = true; job.NS = 0; return SSDC_OK; }
     DecodeArgs g; int iou_f32, tf, cmp_rn;
     SSDC_TRY(build_args(job, ctx->opt[SSDC_OPT_NO_SWEEP] != 0, &g, &iou_f32, &tf, &cmp_rn));
+    g.evict_first = g.sweep && ctx->opt[SSDC_OPT_NO_L2_HINTS] == 0;      // (measured on the image-sweep path: headline 0.229 -> 0.222 ms)
     job.NS = g.NS; job.iou_f32 = iou_f32;
     const size_t elem = (dtype == SSDC_F32) ? 4 : 8;
     const size_t in_bytes = (size_t)B * A * g.W * elem;
