@@ -54,6 +54,19 @@ struct Buf {
         cap = want;
         return SSDC_OK;
     }
+    // grows to exactly `bytes` (no head-room): brings a sibling buffer to the capacity another one already has
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return SSDC_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr; cap = 0;
+            return SSDC_ERR_CUDA;
+        }
+        cap = bytes;
+        return SSDC_OK;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };

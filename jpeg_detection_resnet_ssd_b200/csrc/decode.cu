@@ -488,12 +488,13 @@ __device__ __forceinline__ void floor_slot_flush(FloorSlot* fs, unsigned* __rest
     }
     __syncwarp();
 }
-__device__ __forceinline__ void floor_slot_arm(FloorSlot* fs, int b, float thr, const int* __restrict__ g_floor) {
+// `seen`: the image's published floor bin as lane 0 read it (a CTA that started the image earlier; any earlier snapshot is a
+// valid bound, so the producer loads it one tile ahead and never waits for it in front of a copy it has to issue)
+__device__ __forceinline__ void floor_slot_arm(FloorSlot* fs, int b, float thr, int seen) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int q = 0; q < 8; ++q) fs->hist[lane * 8 + q] = 0u;
     if (lane == 0) {
-        const int seen = *reinterpret_cast<const volatile int*>(&g_floor[b]);      // a CTA that started the image earlier
         const float edge_excl = seen > 0 ? unord32(floor_edge_ord(seen) - 1u) : thr;
         fs->bin = seen;
         fs->thr_excl = edge_excl > thr ? edge_excl : thr;
@@ -539,6 +540,7 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
         int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
         int it = 0, armed = -1;
         const uint64_t pol = g.evict_first ? l2_policy_evict_first() : 0ull;
+        int seen_next = (floors && lane == 0) ? *reinterpret_cast<const volatile int*>(&g_floor[b]) : 0;
         for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
             if (tile_id == g.tiles) { tile_id = 0; ++b; }
             const int s = it % D1_STAGES;
@@ -549,7 +551,7 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
                 // (image b - 2) any more; tile t itself cannot be consumed before its `full` barrier is armed below.
                 FloorSlot* fs = &slots[b & 1];
                 floor_slot_flush(fs, g_hist);
-                floor_slot_arm(fs, b, (float)thr, g_floor);
+                floor_slot_arm(fs, b, (float)thr, seen_next);
                 armed = b;
             }
             if (lane == 0) {
@@ -559,6 +561,8 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
                 mbar_expect_tx(&full[s], bytes);
                 if (g.evict_first) tma_load_1d_hint(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s], pol);
                 else tma_load_1d(smem_raw + (size_t)s * stage_bytes, y + ((size_t)b * A + a0) * W, bytes, &full[s]);
+                // the next tile opens a new image: its published floor is on its way while this stage is being consumed
+                if (floors && tile_id + 1 == g.tiles && t + 1 < t_end) seen_next = *reinterpret_cast<const volatile int*>(&g_floor[b + 1]);
             }
             __syncwarp();
         }
