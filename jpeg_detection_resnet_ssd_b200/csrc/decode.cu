@@ -114,7 +114,9 @@ struct PendingKeys {
     int n_cur, b_cur;              // its keys and their image
     int n_pend, b_pend;            // the other half: keys waiting for their write-out, their image
     int base_pend;                 // lane 31: first reserved slot of the waiting half (result of the atomic)
+    bool crowded;                  // the warp's previous tile: most rows had a candidate (process_tile_sweep walks instead of asking)
 };
+constexpr int D1_COOP_MAX = 10;                // rows with a candidate per warp-tile up to which the warp looks at them together
 __device__ __forceinline__ void retire_pending(PendingKeys& pk, unsigned long long* __restrict__ keys, size_t img_stride) {
     if (pk.n_pend == 0) return;
     const int lane = threadIdx.x & 31;
@@ -228,23 +230,59 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
     // and branches - on the same value)
     const float t = fs ? __shfl_sync(0xffffffffu, *reinterpret_cast<volatile float*>(&fs->thr_excl), 0) : thr;
     int counted = 0;                          // candidates added to the histogram by this call (warp-uniform)
+    bool crowded = pk ? pk->crowded : false;  // most rows of the warp's previous tile had a candidate (warp-uniform)
     // ssd_output_decoder.py:207-209, 32 classes per pass
     for (int c0 = 0; c0 < NS; c0 += 32) {
         const int nc = min(32, NS - c0);
         unsigned mask = 0;
         {
-            // (four classes per trip: the per-class compare is the kernel's base load - one shared-memory read, one
-            // compare, one bit insert; the loop bookkeeping must not double it)
+            // Rows with a candidate are usually rare (a few per warp-tile; fewer still once a score floor stands), so a row
+            // first asks only WHETHER any of its classes passes: the maximum of its confidences (3-input FMNMX, half an
+            // instruction per class; a NaN never wins, and `max > t` holds exactly when some non-NaN class is > t).  The
+            // rows that pass are then looked at by the whole warp, lane <-> class: one shared-memory read, one compare and
+            // one ballot give a row's class mask.  Where most rows pass (dense inputs before the floor bites) that costs
+            // more than every lane walking its own row, so a warp whose last tile was crowded skips the question and walks.
             const float* cf = row + 1 + c0;
-            int c = 0;
+            int npass = 32;
+            if (!crowded) {
+                float m = -INFINITY;
+                if (nc == 20) {                                   // (the VOC layout: straight-line code, 20 reads + 10 FMNMX3)
+#pragma unroll
+                    for (int c = 0; c < 20; c += 2) m = fmaxf(m, fmaxf(cf[c], cf[c + 1]));
+                } else {
+                    int c = 0;
 #pragma unroll 1
-            for (; c + 4 <= nc; c += 4) {
-                const float v0 = cf[c], v1 = cf[c + 1], v2 = cf[c + 2], v3 = cf[c + 3];
-                mask |= ((unsigned)(v0 > t) | ((unsigned)(v1 > t) << 1) | ((unsigned)(v2 > t) << 2) | ((unsigned)(v3 > t) << 3)) << c;
+                    for (; c + 4 <= nc; c += 4) m = fmaxf(fmaxf(m, fmaxf(cf[c], cf[c + 1])), fmaxf(cf[c + 2], cf[c + 3]));
+#pragma unroll 1
+                    for (; c < nc; ++c) m = fmaxf(m, cf[c]);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, valid && m > t);
+                if (pm == 0u) continue;
+                npass = __popc(pm);
+                if (npass <= D1_COOP_MAX) {
+                    const float* wrow = dst + (size_t)(tid - lane) * W + 1 + c0 + (lane < nc ? lane : 0);      // this warp's first row, lane's class
+                    for (unsigned rem = pm; rem; rem &= rem - 1) {
+                        const int r = __ffs(rem) - 1;
+                        const unsigned M = __ballot_sync(0xffffffffu, lane < nc && wrow[(size_t)r * W] > t);
+                        if (lane == r) mask = M;
+                    }
+                }
             }
-            for (; c < nc; ++c) mask |= (unsigned)(cf[c] > t) << c;
+            if (npass > D1_COOP_MAX) {
+                // (four classes per trip: one shared-memory read, one compare, one bit insert per class; the loop
+                // bookkeeping must not double it)
+                int c = 0;
+#pragma unroll 1
+                for (; c + 4 <= nc; c += 4) {
+                    const float v0 = cf[c], v1 = cf[c + 1], v2 = cf[c + 2], v3 = cf[c + 3];
+                    mask |= ((unsigned)(v0 > t) | ((unsigned)(v1 > t) << 1) | ((unsigned)(v2 > t) << 2) | ((unsigned)(v3 > t) << 3)) << c;
+                }
+                for (; c < nc; ++c) mask |= (unsigned)(cf[c] > t) << c;
+                if (!valid) mask = 0;
+                npass = __popc(__ballot_sync(0xffffffffu, mask != 0u));
+            }
+            crowded = npass > D1_COOP_MAX;
         }
-        if (!valid) mask = 0;
         int total = __reduce_add_sync(0xffffffffu, __popc(mask));
         if (total == 0) continue;
         // keys carry the class: [ord32(score) | 255 - class | 2^24 - 1 - anchor]; one slot reservation per warp
@@ -283,6 +321,7 @@ __device__ __forceinline__ void process_tile_sweep(const float* __restrict__ dst
         }
         counted += total;
     }
+    if (pk) pk->crowded = crowded;
     if (fs && counted) {
         unsigned old = 0;
         if (lane == 0) old = atomicAdd(&fs->since, (unsigned)counted);
@@ -576,7 +615,7 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
     // ---- consumer warps ----
     PendingKeys pend;
     pend.buf = pend_base + (size_t)warp * 2 * D1_PEND_HALF;
-    pend.cur = 0; pend.n_cur = 0; pend.b_cur = 0; pend.n_pend = 0; pend.b_pend = 0; pend.base_pend = 0;
+    pend.cur = 0; pend.n_cur = 0; pend.b_cur = 0; pend.n_pend = 0; pend.b_pend = 0; pend.base_pend = 0; pend.crowded = false;
     int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it, ++tile_id) {
