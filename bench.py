@@ -95,6 +95,7 @@ def parse_args():
     ap.add_argument('--enc-lanes', type=int, default=None, help='diagnosis: SSDC_OPT_ENC_LANES of the context')
     ap.add_argument('--d1-ctas', type=int, default=None, help='diagnosis: SSDC_OPT_D1_CTAS of the context')
     ap.add_argument('--no-l2-hints', type=int, default=None, help='diagnosis: SSDC_OPT_NO_L2_HINTS of the context')
+    ap.add_argument('--d1-warps', type=int, default=None, help='diagnosis: SSDC_OPT_D1_WARPS of the context')
     ap.add_argument('--sync-steps', action='store_true', help='diagnosis: synchronise after every warm-up step')
     return ap.parse_args()
 
@@ -402,6 +403,8 @@ class DecodeWorkload(object):
         out = None
         for _ in range(2):
             out = self.e2e_call(self.y)
+        if self.in_bytes < 64e6:
+            steps = max(steps, 100)              # (a call on a small batch is a fraction of a millisecond: a longer loop, stated in `steps`)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -515,6 +518,8 @@ class EncodeWorkload(object):
         y = None
         for _ in range(2):
             y = self.enc(self.gt)
+        if self.out_bytes < 256e6:
+            steps = max(steps, 40)               # (a call on a small batch is 1-2 ms: a longer loop, stated in `steps`)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -830,6 +835,8 @@ def main():
         ctx.set_option('enc_lanes', args.enc_lanes)
     if args.d1_ctas is not None:
         ctx.set_option('d1_ctas', args.d1_ctas)
+    if args.d1_warps is not None:
+        ctx.set_option('d1_warps', args.d1_warps)
     if args.no_l2_hints is not None:
         ctx.set_option('no_l2_hints', args.no_l2_hints)
 

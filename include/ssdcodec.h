@@ -101,7 +101,8 @@ int  ssdc_synchronize(ssdc_ctx* ctx);
 #define SSDC_OPT_D1_CTAS           9  /* resident D1 CTAs per SM (TMA loader); 0 = default                                     */
 #define SSDC_OPT_NO_L2_HINTS       10 /* 1: D1's bulk copies of y_pred carry no L2 eviction hint.  Default: evict_first - the batch
                                          crosses the L2 once and must not displace the keys / histograms D1 leaves for the sweep */
-#define SSDC_OPT_COUNT             11
+#define SSDC_OPT_D1_WARPS          11 /* consumer warps (= 32-row slices of a tile) per D1 CTA; 0 = default (8)                  */
+#define SSDC_OPT_COUNT             12
 int     ssdc_set_option(ssdc_ctx* ctx, int option, int64_t value);
 int64_t ssdc_get_option(const ssdc_ctx* ctx, int option);
 

@@ -24,7 +24,7 @@ CONVERSIONS = {'minmax2centroids': 0, 'centroids2minmax': 1, 'corners2centroids'
                'centroids2corners': 3, 'minmax2corners': 4, 'corners2minmax': 5}
 IOU_OUTER, IOU_ELEMENTWISE = 0, 1
 OPTIONS = {'no_sweep': 0, 'floor_target': 1, 'enc_general': 2, 'enc_no_overlap': 3, 'enc_dense_patch': 4,
-           'loss_no_tma': 5, 'h2d_chunk_mb': 6, 'no_pipeline': 7, 'enc_lanes': 8, 'd1_ctas': 9, 'no_l2_hints': 10}
+           'loss_no_tma': 5, 'h2d_chunk_mb': 6, 'no_pipeline': 7, 'enc_lanes': 8, 'd1_ctas': 9, 'no_l2_hints': 10, 'd1_warps': 11}
 K_NAMES = ['decode_filter', 'plan', 'sort', 'nms', 'merge', 'enc_rowbest', 'enc_match', 'enc_write', 'thin', 'enc_patch']
 K_COUNT = len(K_NAMES)
 

@@ -556,14 +556,15 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
     const int W = g.W, A = g.A;
     const size_t stage_bytes = (((size_t)g.tile_rows * W * sizeof(InT)) + 127) & ~(size_t)127;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncw = (int)(blockDim.x >> 5) - 1;            // consumer warps (one row each lane); the last warp produces
     constexpr bool SWEEPABLE = (sizeof(InT) == 4) && !FAST;
     const bool sweep = SWEEPABLE && g.sweep;
     const bool floors = sweep && g.have_hist;             // score histograms + floor (needs >= D1_STAGES tiles per image, host-checked)
     unsigned long long* pend_base = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)D1_STAGES * stage_bytes);
-    FloorSlot* slots = reinterpret_cast<FloorSlot*>(pend_base + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF);
+    FloorSlot* slots = reinterpret_cast<FloorSlot*>(pend_base + (size_t)ncw * 2 * D1_PEND_HALF);
     if (tid == 0) {
-        for (int s = 0; s < D1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], D1_THREADS / 32); }
-        mbar_init(&done_bar, D1_THREADS / 32);
+        for (int s = 0; s < D1_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ncw); }
+        mbar_init(&done_bar, (uint32_t)ncw);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (floors) { slots[0].image = -1; slots[1].image = -1; }
     }
@@ -574,7 +575,7 @@ decode_filter_tma_kernel(const InT* __restrict__ y, DecodeArgs g, InT thr, int t
     const int per = total_tiles / (int)gridDim.x, extra = total_tiles - per * (int)gridDim.x;
     const int t_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
     const int t_end = t_begin + per + ((int)blockIdx.x < extra ? 1 : 0);
-    if (warp == D1_THREADS / 32) {
+    if (warp == ncw) {
         // ---- producer warp (lane 0 issues the copies; the whole warp serves the floor slots) ----
         int b = t_begin / g.tiles, tile_id = t_begin - b * g.tiles;
         int it = 0, armed = -1;
@@ -2006,11 +2007,13 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
     const size_t row_bytes = (size_t)g.W * sizeof(InT);
     if (d1_tma_ok(y_dev, g, sizeof(InT))) {
         const size_t stage_bytes = (((size_t)g.tile_rows * row_bytes) + 127) & ~(size_t)127;
-        const size_t smem = stage_bytes * D1_STAGES + (size_t)(D1_THREADS / 32) * 2 * D1_PEND_HALF * sizeof(unsigned long long) +
+        const int ncw = (g.tile_rows + 31) / 32;               // consumer warps: one row per thread
+        const unsigned threads = (unsigned)(ncw + 1) * 32;
+        const size_t smem = stage_bytes * D1_STAGES + (size_t)ncw * 2 * D1_PEND_HALF * sizeof(unsigned long long) +
                             2 * sizeof(FloorSlot);
         int ctas_per_sm = (int)((226 * 1024) / (smem + 1024 + 256));
+        if (ctx->opt[SSDC_OPT_D1_CTAS] > 0) max_ctas_per_sm = (int)ctx->opt[SSDC_OPT_D1_CTAS];
         if (ctas_per_sm > max_ctas_per_sm) ctas_per_sm = max_ctas_per_sm;
-        if (ctx->opt[SSDC_OPT_D1_CTAS] > 0 && ctx->opt[SSDC_OPT_D1_CTAS] < ctas_per_sm) ctas_per_sm = (int)ctx->opt[SSDC_OPT_D1_CTAS];
         if (ctas_per_sm < 1) ctas_per_sm = 1;
 #ifdef SSDC_TIMING_KNOBS
         if (const char* e = getenv("SSDC_D1_CTAS")) ctas_per_sm = atoi(e);      // (timing experiments only; not in release builds)
@@ -2020,10 +2023,10 @@ static int launch_d1(ssdc_ctx* ctx, DevCtx* d, const InT* y_dev, const DecodeArg
         if (grid > total_tiles) grid = total_tiles;
         if (fast) {
             SSDC_TRY(ensure_dyn_smem(d->device, (const void*)decode_filter_tma_kernel<InT, true>, smem));
-            decode_filter_tma_kernel<InT, true><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
+            decode_filter_tma_kernel<InT, true><<<(unsigned)grid, threads, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         } else {
             SSDC_TRY(ensure_dyn_smem(d->device, (const void*)decode_filter_tma_kernel<InT, false>, smem));
-            decode_filter_tma_kernel<InT, false><<<(unsigned)grid, D1_TMA_THREADS, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
+            decode_filter_tma_kernel<InT, false><<<(unsigned)grid, threads, smem, st>>>(y_dev, g, thr, (int)total_tiles, seg_count, keys, boxes, aux, g_floor, g_hist);
         }
         SSDC_TRY(check_launch("decode_filter_tma_kernel"));
     } else {
@@ -2410,7 +2413,11 @@ int decode_submit_dev(ssdc_ctx* ctx, DevCtx* d, const void* y_pred, int dtype, i
     if (B == 0) { job.valid = true; job.NS = 0; return SSDC_OK; }
     DecodeArgs g; int iou_f32, tf, cmp_rn;
     SSDC_TRY(build_args(job, ctx->opt[SSDC_OPT_NO_SWEEP] != 0, &g, &iou_f32, &tf, &cmp_rn));
-    g.evict_first = g.sweep && ctx->opt[SSDC_OPT_NO_L2_HINTS] == 0;      // (measured on the image-sweep path: headline 0.229 -> 0.222 ms)
+    g.evict_first = g.sweep && ctx->opt[SSDC_OPT_NO_L2_HINTS] == 0;
+    if (ctx->opt[SSDC_OPT_D1_WARPS] >= 1 && ctx->opt[SSDC_OPT_D1_WARPS] * 32 < g.tile_rows) {      // (diagnosis: smaller tiles, fewer consumer warps per CTA)
+        g.tile_rows = (int)ctx->opt[SSDC_OPT_D1_WARPS] * 32;
+        g.tiles = (int)((job.A + g.tile_rows - 1) / g.tile_rows);
+    }      // (measured on the image-sweep path: headline 0.229 -> 0.222 ms)
     job.NS = g.NS; job.iou_f32 = iou_f32;
     const size_t elem = (dtype == SSDC_F32) ? 4 : 8;
     const size_t in_bytes = (size_t)B * A * g.W * elem;
