@@ -532,3 +532,29 @@ def test_sweep_vs_general_pipeline_randomised(seed, ctx):
             finally:
                 ctx.set_option('floor_target', 0)
             assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), (seed, top_k, target, bias, sigma, thr, iou)
+
+
+@pytest.mark.parametrize('warps,ctas', [(4, 5), (6, 3), (6, 4), (8, 2)])
+def test_d1_tile_shapes_do_not_change_results(warps, ctas, ctx):
+    """The filter kernel's tile shape is a run-time parameter (32 rows per consumer warp, CTAs per SM): every shape - and with
+    it every split of an image over CTAs, every floor history - returns the rows of the default configuration, with and
+    without the L2 eviction hint on the bulk copies."""
+    enc = synth.make_encoder(SSDInputEncoder, 'ssd300')
+    kw = synth.layout_kwargs('ssd300')
+    C = kw['n_classes'] + 1
+    tail = ('centroids', True, kw['img_height'], kw['img_width'], 'half')
+    for bias, thr in ((8.0, 0.01), (4.0, 0.001)):
+        y = synth.synth_y_pred(synth.anchors_of(enc), enc.variances, C, 3, 900 + warps, bg_bias=bias, hot=30)
+        y = np.ascontiguousarray(np.tile(y, (7, 1, 1)))
+        want = product_rows7(*_lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, 200, *tail, ctx=ctx))
+        ctx.set_option('d1_warps', warps)
+        ctx.set_option('d1_ctas', ctas)
+        try:
+            for hints_off in (0, 1):
+                ctx.set_option('no_l2_hints', hints_off)
+                got = product_rows7(*_lib.run_decode(y, _lib.MODE_PER_CLASS, thr, 0.45, 200, *tail, ctx=ctx))
+                assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), (warps, ctas, bias, hints_off)
+        finally:
+            ctx.set_option('d1_warps', 0)
+            ctx.set_option('d1_ctas', 0)
+            ctx.set_option('no_l2_hints', 0)

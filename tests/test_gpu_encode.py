@@ -230,7 +230,7 @@ def test_back_to_back_device_encodes_keep_their_own_ground_truth(ctx):
         ctx.dev_free(d)
 
 
-@pytest.mark.parametrize('lanes', [1, 2, 3])
+@pytest.mark.parametrize('lanes', [1, 2, 3, 6])
 def test_device_encodes_on_lanes_are_ordered_where_they_must_be(ctx, lanes):
     """Device-output encodes run on `enc_lanes` lanes (stream pair + scratch each).  Calls that write the same buffer must
     land in call order (the later call wins, never a mix of one call's template and another's patches), a reader enqueued
