@@ -49,7 +49,7 @@ def _source_hash():
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, 'ssdcodec.h')]
     for f in files:
         with open(f, 'rb') as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())      # (not the absolute path: a snapshot of the tree elsewhere keeps its stamp)
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())
     return h.hexdigest()
