@@ -130,8 +130,6 @@ def init_dist(world, local_rank, backend=None):
     import torch.distributed as dist
     if backend is None:
         backend = 'nccl' if torch.cuda.is_available() else 'gloo'
-    # (NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION / WARN / INFO: keep stdout to the one JSON line)
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     if backend == 'nccl':
         torch.cuda.set_device(local_rank)
         dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local_rank))
