@@ -220,3 +220,22 @@ def test_drop_in_extends_partially_replaced_reference_classes(tmp_path):
              "assert Evaluator is DeviceEvaluator and SSDLoss is DeviceSSDLoss\nprint('ok')\n")
     r = subprocess.run([sys.executable, '-c', code2], capture_output=True, text=True, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
+
+
+def test_build_stamp_survives_a_copy_of_the_tree(built_lib, tmp_path):
+    """The GPU box runs a snapshot of the repository at another path: the prebuilt library must count as current there
+    (the stamp hashes file names and contents, not absolute paths), and a changed source must not."""
+    import shutil
+    import sys
+    src = os.path.join(ROOT, 'jpeg_detection_resnet_ssd_b200')
+    dst = tmp_path / 'snap'
+    shutil.copytree(src, dst / 'jpeg_detection_resnet_ssd_b200', ignore=shutil.ignore_patterns('__pycache__', '*.o'))
+    shutil.copytree(os.path.join(ROOT, 'include'), dst / 'include')
+    code = ('import sys; sys.path.insert(0, %r); from jpeg_detection_resnet_ssd_b200 import build; '
+            'print(build.LIBPATH.startswith(%r), build.is_current())' % (str(dst), str(dst)))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ['True', 'True']
+    with open(dst / 'jpeg_detection_resnet_ssd_b200' / 'csrc' / 'thin.cu', 'a') as fh:
+        fh.write('\n// changed\n')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ['True', 'False']
